@@ -1,0 +1,118 @@
+/* pbf_b200.h — C ABI of the B200-native Position Based Fluids step.
+ *
+ * This is the drop-in boundary for the reference's per-timestep hot path.  The reference
+ * (SsnL/Fluid) has no FFI layer; the seam is `struct Particles` (src/particles.h:105-140):
+ *   Particles::Particles(rest_density)      -> pbf_create        (particles.h:114-116)
+ *   Particles::addParticle(pos, v) x N      -> pbf_upload        (particles.h:118-120)
+ *   Particles::timeStep() / timeStep(dt)    -> pbf_step          (particles.cpp:250-301)
+ *   ps[i]->getPosition()/velocity/
+ *        getLatestDensityEstimate()         -> pbf_download      (particles.h:21,36-42)
+ *   cout "avg rho: a => b" per step         -> pbf_stats         (particles.cpp:267,279,295)
+ *   Particles::estimateDensities()          -> pbf_estimate_densities (particles.cpp:440-444)
+ * INTEGRATION.md shows the ~30-line patch a maintainer of the reference would apply.
+ *
+ * Conventions: plain C, opaque handle, int status codes (0 = PBF_OK), no exceptions cross the
+ * boundary, no global state, one handle = one CUDA device + one stream, a handle is not
+ * thread-safe, the caller owns every host buffer.  Host-side vectors are AoS xyz doubles in
+ * ORIGINAL particle order (the order of addParticle calls), which is what Particles holds.
+ * All device arithmetic is fp32 (see DESIGN.md for the parity contract).
+ */
+#ifndef PBF_B200_H
+#define PBF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbf_handle pbf_handle;
+
+enum {
+  PBF_OK = 0,
+  PBF_ERR_INVALID = 1,       /* bad argument / call order                                  */
+  PBF_ERR_CUDA = 2,          /* a CUDA runtime call failed; see pbf_last_error              */
+  PBF_ERR_NO_DEVICE = 3,     /* no usable CUDA device: there is NO CPU fallback             */
+  PBF_ERR_CAPACITY = 4,      /* neighbour / cell / halo capacity exceeded (never truncates) */
+  PBF_ERR_DOMAIN = 5         /* non-finite particle state, or migration beyond one slab     */
+};
+
+/* XSPH ordering.  The reference applies updateVelocity + XSPH fused per
+ * particle in index order (particles.cpp:285-288, quirk Q11); the parallel path is Jacobi. */
+enum { PBF_XSPH_JACOBI = 0, PBF_XSPH_REFERENCE_ORDER = 1 };
+
+/* Runtime parameters.  Defaults (pbf_default_params) are the reference's private macros,
+ * particles.cpp:10-44, and the hard-coded Cornell box of clamp()/clamp_response()
+ * (particles.cpp:59-83,96-131). */
+typedef struct PbfParams {
+  double h;             /* SPH support radius H                 0.3    particles.cpp:26      */
+  double dt;            /* DEFAULT_DELTA_T                      0.016  particles.cpp:24      */
+  double rest_density;  /* rho0 (from XML <density>, via stof)  1000   particles.h:114       */
+  double eps_relax;     /* EPSILON in lambda denominator        2      particles.cpp:36      */
+  double k_corr;        /* K, artificial pressure coefficient   1e-4   particles.cpp:38      */
+  double dq_ratio;      /* |dq| / H of the tensile term         0.1    particles.cpp:151     */
+  double visc_c;        /* C, XSPH viscosity                    1e-3   particles.cpp:44      */
+  double vort_eps;      /* VORTICITY_EPSILON                    1e-3   particles.cpp:42      */
+  double gravity_y;     /* velocity.y += gravity_y*dt           -10    particles.cpp:180     */
+  int32_t n_corr;       /* N, artificial pressure exponent      4      particles.cpp:40      */
+  int32_t iterations;   /* NEWTON_NUM_STEPS                     12     particles.cpp:34      */
+  double box_min[3];    /* collision box, hard clamp lower      {-1,0,-1}   particles.cpp:81-83 */
+  double box_max[3];    /* hard clamp upper                     {1,1.49,1}  particles.cpp:81-83 */
+  double y_light;       /* virtual plane y (light)              1.49   particles.cpp:69,106  */
+  double z_front;       /* virtual plane z (open front)         1.0    particles.cpp:60,97   */
+  int32_t xsph_mode;    /* PBF_XSPH_*; the GPU path implements JACOBI only                   */
+  int32_t enable_vorticity; /* 1: vorticity confinement (particles.cpp:236-244)              */
+  int32_t enable_xsph;      /* 1: XSPH viscosity       (particles.cpp:229,233)               */
+  int32_t reserved;
+} PbfParams;
+
+void pbf_default_params(PbfParams* p);
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int  pbf_create(const PbfParams* params, int device_id, pbf_handle** out);
+void pbf_destroy(pbf_handle* h);
+const char* pbf_last_error(pbf_handle* h);      /* valid until the next call on h            */
+int  pbf_device_count(void);                    /* 0 when no CUDA device is visible          */
+
+/* ---- state in / out (host buffers, original order, doubles) ----------------------------- */
+int  pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz);
+int  pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density); /* syncs; any pointer may be NULL */
+size_t pbf_num_particles(pbf_handle* h);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+int  pbf_step(pbf_handle* h, int n_steps);      /* enqueues n_steps * timeStep(dt); asynchronous */
+int  pbf_sync(pbf_handle* h);                   /* waits; reports deferred device-side errors    */
+int  pbf_estimate_densities(pbf_handle* h);     /* load-time density incl. self (Q1, a15)        */
+/* avg density after the first lambda pass and after the finalize pass of the LAST step
+ * (the two numbers the reference prints), and the device time of the last pbf_step call. */
+int  pbf_stats(pbf_handle* h, double* avg_rho_first_iter, double* avg_rho_final, double* last_call_ms);
+
+/* ---- device-resident I/O (bench "value" leg; fp32 xyz AoS device pointers, original order) */
+int  pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz);
+int  pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, float* d_density);
+
+/* ---- parity / debug ---------------------------------------------------------------------- */
+/* Order-independent 64-bit digest and size of each particle's frozen neighbour set of the last
+ * step, in ORIGINAL indices (sum over neighbours j of mix64(j)); see oracle/pbf_oracle.hpp. */
+int  pbf_debug_neighbor_digest(pbf_handle* h, uint64_t* per_particle_digest, uint32_t* per_particle_count);
+/* CSR of the frozen neighbour sets, original indices, ascending within a row (small N). */
+int  pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr /*n+1*/, uint32_t* col_idx, size_t col_cap);
+/* Intermediate per-particle arrays of the last step, original order, as doubles. */
+enum { PBF_ARRAY_XSTAR = 0 /*n*3 predicted/corrected positions*/, PBF_ARRAY_LAMBDA = 1 /*n*/,
+       PBF_ARRAY_VORTICITY = 2 /*n*3*/, PBF_ARRAY_XPRED = 3 /*n*3 x* right after predict+collide*/ };
+int  pbf_debug_download_array(pbf_handle* h, int which, double* out);
+/* Number of kernel launches issued by this handle so far (bench "gpu_launches"). */
+uint64_t pbf_launch_count(pbf_handle* h);
+/* Per-kernel device time (CUDA events) accumulated since the last reset; names are static.
+ * Enabling profiling serialises the stream with events; off by default. */
+int  pbf_profile_enable(pbf_handle* h, int on);
+int  pbf_profile_get(pbf_handle* h, int max, const char** names, double* total_ms, uint64_t* launches);
+
+/* ---- slab decomposition (one process per GPU; x-slabs) ---------------------
+ * See fluid_b200/slab.py for the protocol; declared in pbf_b200_slab.h. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBF_B200_H */

@@ -1,0 +1,461 @@
+// TEST INFRASTRUCTURE ONLY — CPU restatement of the reference PBF step (SsnL/Fluid).
+//
+// Nothing under fluid_b200/ (the product) includes, links or calls this file.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and
+// only as the checker / the CPU baseline.
+//
+// Parity status: PINNED.  The reference has no tests or golden vectors for this path
+// (SURVEY.md §4), so the pin is the unmodified reference itself, compiled headlessly by
+// oracle/Makefile into oracle/_ref/ref_harness: Oracle<double>(XSPH reference order, triangle
+// walls) reproduces its full state and ordered neighbour lists bit-for-bit
+// (tests/test_oracle_vs_reference.py; committed fixtures in tests/golden/).
+//
+// Each function cites the reference lines it restates.  Arithmetic ORDER is part of the
+// contract (SURVEY.md §8c "rules"): Vector3D / scalar multiplies by the reciprocal
+// (CGL/include/CGL/vector3D.h:79-82,100-102), unit() multiplies by 1/sqrt (121-124), intpow<e>
+// is ((1*b)*b)... (src/bsdf.h:49-57), norm2 is x*x+y*y+z*z left to right (114-116).
+// Compile with -ffp-contract=off.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/pbf_b200.h"
+
+namespace pbf_oracle {
+
+// ---- CGL::Vector3D semantics (vector3D.h:54-150), generic in the scalar type ------------------
+template <class R>
+struct V3 {
+  R x, y, z;
+  V3() : x(0), y(0), z(0) {}
+  V3(R x_, R y_, R z_) : x(x_), y(y_), z(z_) {}
+  V3 operator-() const { return V3(-x, -y, -z); }
+  V3 operator+(const V3& v) const { return V3(x + v.x, y + v.y, z + v.z); }
+  V3 operator-(const V3& v) const { return V3(x - v.x, y - v.y, z - v.z); }
+  V3 operator*(R c) const { return V3(x * c, y * c, z * c); }           // right scalar mult
+  V3 operator/(R c) const { const R rc = R(1) / c; return V3(rc * x, rc * y, rc * z); }
+  void operator+=(const V3& v) { x += v.x; y += v.y; z += v.z; }
+  void operator*=(R c) { x *= c; y *= c; z *= c; }
+  void operator/=(R c) { (*this) *= (R(1) / c); }
+  R norm() const { return std::sqrt(x * x + y * y + z * z); }
+  R norm2() const { return x * x + y * y + z * z; }
+  V3 unit() const { R rn = R(1) / std::sqrt(x * x + y * y + z * z); return V3(rn * x, rn * y, rn * z); }
+  R& operator[](int i) { return (&x)[i]; }
+  const R& operator[](int i) const { return (&x)[i]; }
+};
+template <class R> inline V3<R> operator*(R c, const V3<R>& v) { return V3<R>(c * v.x, c * v.y, c * v.z); }
+template <class R> inline R dot(const V3<R>& u, const V3<R>& v) { return u.x * v.x + u.y * v.y + u.z * v.z; }
+template <class R> inline V3<R> cross(const V3<R>& u, const V3<R>& v) {
+  return V3<R>(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+template <class R> inline R intpow(R b, int e) { R r = R(1); for (int i = 0; i < e; i++) r = r * b; return r; }
+
+// std::min/std::max as the reference uses them (NaN behaviour included)
+template <class R> inline R rmin(R a, R b) { return (b < a) ? b : a; }
+template <class R> inline R rmax(R a, R b) { return (a < b) ? b : a; }
+
+inline uint64_t mix64(uint64_t j) {   // digest of a neighbour index (order-independent sum)
+  uint64_t z = j + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+enum { COLLIDE_REFERENCE_TRIANGLES = 0, COLLIDE_ANALYTIC_BOX = 1 };
+enum { SEARCH_BRUTE = 0, SEARCH_GRID = 1 };
+
+// ---- wall triangles of the reference scene (dae/sky/CBempty.dae:229-444 as exact quads) --------
+template <class R>
+struct Tri { V3<R> p1, p2, p3, n; };
+
+template <class R>
+struct Oracle {
+  typedef V3<R> V;
+  PbfParams P;
+  int collision_mode, search_mode;
+  // parameters in working precision (particles.cpp:24-44)
+  R H, H2, DT, RHO0, EPS_RELAX, KCORR, VISC, VORT_EPS, GRAV, EPS_D, TSCALE;
+  int NCORR, ITERS;
+  V bmin, bmax; R YL, ZF;
+  std::vector<Tri<R>> tris;
+
+  size_t n = 0;
+  std::vector<V> pos, npos, vel, vort, xpred;
+  std::vector<R> dens, lam;
+  std::vector<uint32_t> row_ptr;
+  std::vector<int32_t> col;
+  double avg_rho_first = 0, avg_rho_final = 0, sim_time = 0;
+
+  Oracle(const PbfParams& p, int cmode, int smode) : P(p), collision_mode(cmode), search_mode(smode) {
+    H = R(p.h); H2 = H * H;   // literal H2 0.09 == 0.3*0.3 in fp64 and fp32 (tests assert it)
+    DT = R(p.dt); RHO0 = R(p.rest_density); EPS_RELAX = R(p.eps_relax); KCORR = R(p.k_corr);
+    VISC = R(p.visc_c); VORT_EPS = R(p.vort_eps); GRAV = R(p.gravity_y); EPS_D = R(1e-11);  // misc.h:11
+    NCORR = p.n_corr; ITERS = p.iterations;
+    bmin = V(R(p.box_min[0]), R(p.box_min[1]), R(p.box_min[2]));
+    bmax = V(R(p.box_max[0]), R(p.box_max[1]), R(p.box_max[2]));
+    YL = R(p.y_light); ZF = R(p.z_front);
+    // particles.cpp:151  tensile_instability_scale = 1 / poly6(0,0,0.1*H)
+    TSCALE = R(1) / poly6(V(R(0), R(0), R(p.dq_ratio) * H));
+    build_walls();
+  }
+
+  void add_quad(V a, V b, V c, V d, V nn) {
+    tris.push_back(Tri<R>{a, b, c, nn});
+    tris.push_back(Tri<R>{a, c, d, nn});
+  }
+  // Walls generalised from the Cornell box: ceiling 0.01 above y_light (1.5 vs 1.49), floor,
+  // x-, x+, back (z-); the front (z+) is open (virtual plane).  For the default params these are
+  // exactly the quads of oracle/ref_harness/harness.cpp.
+  void build_walls() {
+    R x0 = bmin.x, x1 = bmax.x, y0 = bmin.y, y1 = R(P.box_max[1] + 0.01), z0 = bmin.z, z1 = bmax.z;
+    add_quad(V(x1, y1, z0), V(x0, y1, z0), V(x0, y1, z1), V(x1, y1, z1), V(0, -1, 0));
+    add_quad(V(x1, y0, z0), V(x1, y0, z1), V(x0, y0, z1), V(x0, y0, z0), V(0, 1, 0));
+    add_quad(V(x0, y1, z0), V(x0, y0, z0), V(x0, y0, z1), V(x0, y1, z1), V(1, 0, 0));
+    add_quad(V(x1, y1, z1), V(x1, y0, z1), V(x1, y0, z0), V(x1, y1, z0), V(-1, 0, 0));
+    add_quad(V(x1, y1, z0), V(x1, y0, z0), V(x0, y0, z0), V(x0, y1, z0), V(0, 0, 1));
+  }
+
+  // ---- kernels: particles.cpp:134-149 ----------------------------------------------------------
+  R poly6(const V& r) const {
+    R r2 = r.norm2();
+    if (r2 >= H2) return R(0);
+    R t = H2 - r2;
+    return R(1.56668147106) * intpow(t, 3) / intpow(H, 9);
+  }
+  V grad_spiky(const V& r) const {
+    R rl = r.norm();
+    if (rl >= H || rl < EPS_D) return V();
+    // -3 * 4.77... * intpow<2>(H - r_l) * r / (intpow<6>(H) * r_l)
+    R s = R(-3 * 4.774648292756860) * intpow(H - rl, 2);
+    return (s * r) / (intpow(H, 6) * rl);
+  }
+
+  // ---- ray / triangle (static_scene/marching_triangle.cpp:21-73), segment [0, max_t] -----------
+  bool tri_hit(const Tri<R>& T, const V& o, const V& d, R& max_t, V* nrm) const {
+    V e1 = T.p2 - T.p1, e2 = T.p3 - T.p1, s = o - T.p1;
+    V s1 = cross(d, e2), s2 = cross(s, e1);
+    R dd = dot(s1, e1);
+    if (dd == 0) return false;
+    R t = dot(s2, e2) / dd;
+    if ((t < R(0)) || (t > max_t)) return false;
+    R u = dot(s1, s) / dd, v = dot(s2, d) / dd, w = R(1) - u - v;
+    if ((u < 0) || (u > 1) || (v < 0) || (v > 1) || (w < 0) || (w > 1)) return false;
+    max_t = t;
+    if (nrm) *nrm = w * T.n + u * T.n + v * T.n;
+    return true;
+  }
+  // nearest hit (bvh.cpp:165-192 visits every primitive the boxes let through; each hit shrinks
+  // max_t) and any hit (bvh.cpp:142-163).  Inside the convex box a segment meets at most one
+  // wall, so box culling and visiting order cannot change the answer; verified bit-exactly
+  // against the compiled reference.
+  bool scene_hit(const V& o, const V& d, R& max_t, V* nrm) const {
+    bool hit = false;
+    for (const Tri<R>& T : tris) if (tri_hit(T, o, d, max_t, nrm)) { hit = true; if (!nrm) return true; }
+    return hit;
+  }
+
+  // ---- analytic box walls with the fp32 contact rules ------------------------
+  // one-sided planes (hit only when moving into the wall), exact axis normals, t >= 0.
+  // skip_axis/skip_side: the plane currently being slid on is never re-tested.
+  bool box_hit(const V& o, const V& d, R& max_t, int* axis, int* side, int skip_axis, int skip_side) const {
+    bool hit = false;
+    // order x-, x+, y-, z- ; "t <= max_t" like the reference's acceptance test
+    const int ax[4] = {0, 0, 1, 2}; const int sd[4] = {0, 1, 0, 0};
+    for (int w = 0; w < 4; w++) {
+      int a = ax[w], s = sd[w];
+      if (a == skip_axis && s == skip_side) continue;
+      R plane = s ? bmax[a] : bmin[a];
+      R da = d[a];
+      if (s ? (da > 0) : (da < 0)) {
+        R t = (plane - o[a]) / da;
+        if (t < R(0)) t = R(0);
+        if (t <= max_t) { max_t = t; hit = true; *axis = a; *side = s; }
+      }
+    }
+    return hit;
+  }
+
+  void hard_clamp(V& p) const {   // particles.cpp:81-83 / 129-131
+    p.x = rmax(bmin.x + EPS_D, rmin(bmax.x - EPS_D, p.x));
+    p.y = rmax(bmin.y + EPS_D, rmin(bmax.y - EPS_D, p.y));
+    p.z = rmax(bmin.z + EPS_D, rmin(bmax.z - EPS_D, p.z));
+  }
+
+  // particles.cpp:51-84 (respond=false) and 87-132 (respond=true).
+  void collide(V& p, const V& delta_p, bool respond) const {
+    R total_l = delta_p.norm(), l = total_l;
+    if (l <= EPS_D) return;
+    V d = delta_p / l;
+    bool virt = false;
+    if (collision_mode == COLLIDE_REFERENCE_TRIANGLES) {
+      if (d.z != R(0)) { R pt = (ZF - p.z) / d.z; if (pt > R(0) && pt < l) { l = pt; virt = true; } }
+      if (d.y != R(0)) { R pt = (YL - p.y) / d.y; if (pt > R(0) && pt < l) { l = pt; virt = true; } }
+      R max_t = l; V nrm;
+      bool hit = scene_hit(p, d, max_t, respond ? &nrm : nullptr);
+      if (hit || virt) {
+        p += (max_t - EPS_D) * d;
+        if (respond && dot(d, nrm) > R(-1) && !virt) {   // slide once (particles.cpp:118-124)
+          d = (delta_p - dot(delta_p, nrm) * nrm).unit();
+          R mt = (total_l - max_t) * R(0.5);
+          V n2;
+          scene_hit(p, d, mt, &n2);
+          p += (mt - EPS_D) * d;
+        }
+      } else {
+        p += delta_p;
+      }
+    } else {
+      // sticky virtual planes: d>0 && pt>=0 (fp64 never has pt==0; fp32 does)
+      if (d.z > R(0)) { R pt = (ZF - p.z) / d.z; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
+      if (d.y > R(0)) { R pt = (YL - p.y) / d.y; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
+      R max_t = l; int axis = -1, side = 0;
+      bool hit = box_hit(p, d, max_t, &axis, &side, -1, 0);
+      if (hit || virt) {
+        p += (max_t - EPS_D) * d;
+        if (respond && hit && !virt) {
+          // exact axis normal n = +-e_axis: dot(d,n) > -1  <=>  d is not exactly anti-normal
+          R dn = side ? -d[axis] : d[axis];
+          V tang = delta_p; tang[axis] = R(0);   // delta - dot(delta,n) n, exactly
+          if (dn > R(-1) && tang.norm2() > R(0)) {
+            V d2 = tang.unit();
+            R mt = (total_l - max_t) * R(0.5);
+            int a2 = -1, s2 = 0;
+            box_hit(p, d2, mt, &a2, &s2, axis, side);
+            p += (mt - EPS_D) * d2;
+          }
+        }
+      } else {
+        p += delta_p;
+      }
+    }
+    hard_clamp(p);
+  }
+
+  // ---- state ------------------------------------------------------------------------------------
+  void upload(size_t n_, const double* p, const double* v) {
+    n = n_;
+    pos.resize(n); npos.resize(n); vel.resize(n); vort.assign(n, V()); xpred.resize(n);
+    dens.assign(n, R(0)); lam.assign(n, R(0));
+    for (size_t i = 0; i < n; i++) {
+      pos[i] = V(R(p[3*i]), R(p[3*i+1]), R(p[3*i+2]));
+      npos[i] = pos[i];
+      vel[i] = V(R(v[3*i]), R(v[3*i+1]), R(v[3*i+2]));
+    }
+    row_ptr.assign(n + 1, 0); col.clear();
+  }
+
+  // particles.cpp:440-444 + 158-163: density over ALL particles including self (Q1)
+  void estimate_densities() {
+    build_neighbors(pos, /*include_self=*/true);
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; i++) {
+      R d = R(0);
+      for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) d += poly6(pos[col[k]] - pos[i]);
+      dens[i] = d;
+    }
+  }
+
+  // particles.cpp:258-265: inclusive predicate on predicted positions, ascending index lists,
+  // self excluded (the reference's i<j double loop).  Grid search = conservative binning + the
+  // same predicate + ascending sort, so both searches give identical lists.
+  // NOTE estimate_densities() sums poly6 over all particles; particles with r2 >= H2 add exactly
+  // 0, so restricting to r2 <= H2 (and including self) leaves the sum bit-identical.
+  void build_neighbors(const std::vector<V>& x, bool include_self) {
+    std::vector<uint32_t> cnt(n + 1, 0);
+    if (search_mode == SEARCH_BRUTE) {
+      std::vector<std::vector<int32_t>> lists(n);
+      for (size_t i = 0; i < n; i++) {
+        if (include_self) lists[i].push_back((int32_t)i);
+        for (size_t j = i + 1; j < n; j++)
+          if ((x[i] - x[j]).norm2() <= H2) { lists[i].push_back((int32_t)j); lists[j].push_back((int32_t)i); }
+      }
+      col.clear();
+      for (size_t i = 0; i < n; i++) {
+        std::sort(lists[i].begin(), lists[i].end());
+        row_ptr[i] = (uint32_t)col.size();
+        col.insert(col.end(), lists[i].begin(), lists[i].end());
+      }
+      row_ptr[n] = (uint32_t)col.size();
+      return;
+    }
+    // uniform grid, cell edge slightly larger than H, binning in double
+    const double cs = double(H) * 1.001;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < n; i++) for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], (double)x[i][a]); hi[a] = std::max(hi[a], (double)x[i][a]);
+    }
+    long dim[3];
+    for (int a = 0; a < 3; a++) dim[a] = (long)std::floor((hi[a] - lo[a]) / cs) + 1;
+    const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+    std::vector<uint32_t> cstart(ncell + 1, 0), cellof(n);
+    auto cell_of = [&](const V& p, long c[3]) {
+      for (int a = 0; a < 3; a++) {
+        c[a] = (long)std::floor(((double)p[a] - lo[a]) / cs);
+        c[a] = std::max(0l, std::min(dim[a] - 1, c[a]));
+      }
+    };
+    for (size_t i = 0; i < n; i++) {
+      long c[3]; cell_of(x[i], c);
+      cellof[i] = (uint32_t)((c[0] * dim[1] + c[1]) * dim[2] + c[2]);
+      cstart[cellof[i] + 1]++;
+    }
+    for (size_t c = 0; c < ncell; c++) cstart[c + 1] += cstart[c];
+    std::vector<uint32_t> fill(cstart.begin(), cstart.end() - 1), items(n);
+    for (size_t i = 0; i < n; i++) items[fill[cellof[i]]++] = (uint32_t)i;   // ascending within a cell
+
+    auto visit = [&](size_t i, std::vector<int32_t>& out) {
+      out.clear();
+      long c[3]; cell_of(x[i], c);
+      for (long dx = -1; dx <= 1; dx++) for (long dy = -1; dy <= 1; dy++) for (long dz = -1; dz <= 1; dz++) {
+        long cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= dim[0] || cy >= dim[1] || cz >= dim[2]) continue;
+        size_t cc = (size_t)((cx * dim[1] + cy) * dim[2] + cz);
+        for (uint32_t k = cstart[cc]; k < cstart[cc + 1]; k++) {
+          size_t j = items[k];
+          if (j == i) { if (include_self) out.push_back((int32_t)j); continue; }
+          // the reference evaluates ps[min]-ps[max]; the square is symmetric
+          V d = (i < j) ? (x[i] - x[j]) : (x[j] - x[i]);
+          if (d.norm2() <= H2) out.push_back((int32_t)j);
+        }
+      }
+      std::sort(out.begin(), out.end());
+    };
+    #pragma omp parallel
+    {
+      std::vector<int32_t> tmp;
+      #pragma omp for schedule(dynamic, 256)
+      for (long i = 0; i < (long)n; i++) { visit((size_t)i, tmp); cnt[i + 1] = (uint32_t)tmp.size(); }
+    }
+    row_ptr[0] = 0;
+    for (size_t i = 0; i < n; i++) row_ptr[i + 1] = row_ptr[i] + cnt[i + 1];
+    col.resize(row_ptr[n]);
+    #pragma omp parallel
+    {
+      std::vector<int32_t> tmp;
+      #pragma omp for schedule(dynamic, 256)
+      for (long i = 0; i < (long)n; i++) {
+        visit((size_t)i, tmp);
+        std::copy(tmp.begin(), tmp.end(), col.begin() + row_ptr[i]);
+      }
+    }
+  }
+
+  // ---- one time step: particles.cpp:250-297 -----------------------------------------------------
+  void step() {
+    sim_time += double(DT);
+    // A: applyForceVelocity (175-183)
+    #pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+      vel[i].y -= R(-GRAV) * DT;          // velocity.y -= 10 * delta_t   (GRAV = -10)
+      npos[i] = pos[i];
+      collide(npos[i], vel[i] * DT, true);
+      xpred[i] = npos[i];
+    }
+    // B: frozen neighbour lists on predicted positions (258-265)
+    build_neighbors(npos, false);
+    // D: Newton iterations (271-284)
+    std::vector<V> snap(n);
+    for (int it = 0; it < ITERS; it++) {
+      // D1 newtonStepCalculateLambda (185-204)
+      #pragma omp parallel for schedule(dynamic, 256)
+      for (long i = 0; i < (long)n; i++) {
+        R density = R(0), denom = R(0);
+        V grad_i;
+        for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+          V r = npos[i] - npos[col[k]];
+          R w = poly6(r);
+          V g = grad_spiky(r);
+          density += w;
+          g /= RHO0;
+          grad_i += g;
+          denom += g.norm2();
+        }
+        R c_i = density / RHO0 - R(1);
+        denom += grad_i.norm2();
+        dens[i] = density;
+        lam[i] = -c_i / (denom + EPS_RELAX);
+      }
+      if (it == 0) {
+        double ds = 0; for (size_t i = 0; i < n; i++) ds += double(dens[i]);
+        avg_rho_first = n ? ds / double(n) : 0.0;
+      }
+      // D2 newtonStepUpdatePosition (206-213).  The reference reads per-neighbour caches
+      // (s_corr, grad_w) filled in D1 from the pre-update positions; recomputing them from a
+      // snapshot of those positions gives the same bits without 28 B/pair of cache.
+      snap = npos;
+      #pragma omp parallel for schedule(dynamic, 256)
+      for (long i = 0; i < (long)n; i++) {
+        V dp;
+        for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+          int j = col[k];
+          V r = snap[i] - snap[j];
+          R w = poly6(r);
+          R s_corr = -KCORR * intpow(w * TSCALE, NCORR);
+          V g = grad_spiky(r);
+          dp += (lam[i] + lam[j] + s_corr) * g;
+        }
+        dp /= RHO0;
+        collide(npos[i], dp, false);
+      }
+    }
+    // E: updateVelocity + calculateVorticityApplyXSPHViscosity (215-234, loop 285-288)
+    std::vector<V> gradw;   // not cached: recomputed in F from the same positions
+    if (P.xsph_mode == PBF_XSPH_REFERENCE_ORDER) {
+      for (size_t i = 0; i < n; i++) {   // strictly sequential (quirk Q11)
+        vel[i] = (npos[i] - pos[i]) / DT;
+        pass_e(i, vel, vel);
+      }
+    } else {
+      std::vector<V> vnew(n);
+      #pragma omp parallel for schedule(static)
+      for (long i = 0; i < (long)n; i++) vel[i] = (npos[i] - pos[i]) / DT;
+      vnew = vel;
+      #pragma omp parallel for schedule(dynamic, 256)
+      for (long i = 0; i < (long)n; i++) pass_e((size_t)i, vel, vnew);
+      vel.swap(vnew);
+    }
+    // F: applyVorticity + updatePosition (236-248, loop 290-294)
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; i++) {
+      if (P.enable_vorticity) {
+        V gv;
+        for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+          int j = col[k];
+          gv += vort[j].norm() * grad_spiky(npos[i] - npos[j]);
+        }
+        if (gv.norm() > EPS_D) vel[i] += (DT * VORT_EPS) * cross(gv.unit(), vort[i]);
+      }
+    }
+    double ds = 0;
+    for (size_t i = 0; i < n; i++) { ds += double(dens[i]); pos[i] = npos[i]; }
+    avg_rho_final = n ? ds / double(n) : 0.0;
+  }
+
+  // body of calculateVorticityApplyXSPHViscosity for particle i: reads vin, writes vout[i]
+  void pass_e(size_t i, const std::vector<V>& vin, std::vector<V>& vout) {
+    V w_i, visc;
+    R density = R(0);
+    const V vi = vin[i];
+    for (uint32_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+      int j = col[k];
+      V v_ij = vin[j] - vi;
+      V r = npos[i] - npos[j];
+      V g = grad_spiky(r);
+      w_i += cross(v_ij, g);
+      R w = poly6(r);
+      visc += v_ij * w;
+      density += w;
+    }
+    vort[i] = w_i;
+    dens[i] = density;
+    V out = vi;
+    if (P.enable_xsph) out += VISC * visc;
+    vout[i] = out;
+  }
+};
+
+}  // namespace pbf_oracle

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+Needs /root/reference and oracle/_ref/ref_harness (make -C oracle ref).  The GPU box has neither;
+it only reads the committed .npz files.  Re-run after changing the harness:  python tests/golden/make_golden.py
+
+Fixtures
+  scene_<name>.npz        inputs of the reference's shipped scenes (particles/p.xml, particles/spheres_p.xml)
+                          parsed like Application::load_particles (application.cpp:302-344)
+  ref_<name>.npz          reference output for 20 steps of timeStep(): sha256[:16] of <f8[N,7] per step,
+                          coordinate sums, directed pair counts, the "avg rho: a => b" lines the reference
+                          prints, full state at steps 0/1/19 and the ordered neighbour CSR of step 0
+  ref_jitter_<name>.npz   same for jittered pgen-style inputs (lattice + U(-0.001,0.001),
+                          default_rng(1234)) — the inputs used for fp32-vs-fp64 tolerance checks
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from helpers import (GOLDEN, REFERENCE, load_xml_scene, pgen_two_blocks, lattice_block, read_dump,
+                     ref_harness_path, state_sha, write_bin_scene)
+
+STEPS = 20
+KEEP = (0, 1, 19)
+
+
+def run_reference(pos, vel, rho0, steps):
+    with tempfile.TemporaryDirectory() as td:
+        scene = os.path.join(td, "scene.bin"); dump = os.path.join(td, "dump.bin")
+        write_bin_scene(scene, pos, vel, rho0)
+        subprocess.run([ref_harness_path(), "--bin", scene, "--steps", str(steps), "--out", dump, "--quiet"], check=True)
+        log = open(dump + ".log").read()
+        return read_dump(dump), log
+
+
+def pack(dump, log, keep):
+    lines = re.findall(r"avg rho: (\S+) => (\S+)", log)
+    out = dict(
+        sha=np.array([state_sha(d["state"][:, 0:3], d["state"][:, 3:6], d["state"][:, 6]) for d in dump]),
+        sums=np.array([d["state"][:, 0:3].sum(axis=0) for d in dump]),
+        pairs=np.array([len(d["col"]) for d in dump], dtype=np.int64),
+        avg_rho_text=np.array(lines),
+        keep=np.array(keep, dtype=np.int64),
+    )
+    for s in keep:
+        out[f"state_{s}"] = dump[s]["state"][:, :7].copy()
+    out["nbr_counts_0"] = dump[0]["counts"].copy()
+    out["nbr_col_0"] = dump[0]["col"].copy()
+    return out
+
+
+def jitter_scenes():
+    """name -> (pos, vel, rho0); all inside the reference's hard-coded Cornell box."""
+    pos, vel, rho0 = pgen_two_blocks()
+    rng = np.random.default_rng(1234)
+    two = pos + rng.uniform(-0.001, 0.001, size=pos.shape)
+    # p.xml-like sparse block: 12x5x12, spacing 0.15
+    pb, vb = lattice_block(12, 5, 12, origin=(-0.9, 0.5, -0.9), spacing=0.15, v0=(0, -0.01, 0), jitter=0.0015, seed=1234)
+    # block resting on the floor against two walls: exercises floor/wall contacts and the slide
+    pc, vc = lattice_block(8, 10, 8, origin=(-0.97, 0.03, -0.97), spacing=0.1, v0=(-0.5, -1.0, -0.25), jitter=0.001, seed=99)
+    # block thrown at the open front / light planes (virtual planes z=1, y=1.49)
+    pd, vd = lattice_block(6, 6, 6, origin=(0.2, 0.95, 0.45), spacing=0.1, v0=(0.3, 2.5, 3.0), jitter=0.001, seed=7)
+    return {
+        "two_blocks": (two, vel, rho0),
+        "sparse": (pb, vb, 150.0),
+        "corner": (pc, vc, 700.0),
+        "front": (pd, vd, 700.0),
+    }
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name in ("p", "spheres_p"):
+        pos, vel, rho0 = load_xml_scene(os.path.join(REFERENCE, "particles", name + ".xml"))
+        np.savez_compressed(os.path.join(GOLDEN, f"scene_{name}.npz"), pos=pos, vel=vel, rho0=rho0)
+        dump, log = run_reference(pos, vel, rho0, STEPS)
+        np.savez_compressed(os.path.join(GOLDEN, f"ref_{name}.npz"), **pack(dump, log, KEEP))
+        print(name, pos.shape[0], "sha[0,1,19] =", [state_sha(dump[s]["state"][:, 0:3], dump[s]["state"][:, 3:6], dump[s]["state"][:, 6]) for s in KEEP])
+    for name, (pos, vel, rho0) in jitter_scenes().items():
+        dump, log = run_reference(pos, vel, rho0, 6)
+        np.savez_compressed(os.path.join(GOLDEN, f"ref_jitter_{name}.npz"), pos=pos, vel=vel, rho0=rho0, **pack(dump, log, (0, 1, 5)))
+        print("jitter", name, pos.shape[0], "pairs", [len(d["col"]) for d in dump])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,241 @@
+"""Test-side helpers: ctypes view of the CPU oracle (oracle/liboracle.so), readers for the
+reference-harness dump format, scene loaders and synthetic generators.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this module; the product
+package (fluid_b200/) never does.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+COLLIDE_TRIANGLES, COLLIDE_BOX = 0, 1
+SEARCH_BRUTE, SEARCH_GRID = 0, 1
+XSPH_JACOBI, XSPH_REFERENCE = 0, 1
+ARRAY_XSTAR, ARRAY_LAMBDA, ARRAY_VORTICITY, ARRAY_XPRED = 0, 1, 2, 3
+
+
+class PbfParams(C.Structure):
+    """Mirror of include/pbf_b200.h::PbfParams."""
+    _fields_ = [
+        ("h", C.c_double), ("dt", C.c_double), ("rest_density", C.c_double),
+        ("eps_relax", C.c_double), ("k_corr", C.c_double), ("dq_ratio", C.c_double),
+        ("visc_c", C.c_double), ("vort_eps", C.c_double), ("gravity_y", C.c_double),
+        ("n_corr", C.c_int32), ("iterations", C.c_int32),
+        ("box_min", C.c_double * 3), ("box_max", C.c_double * 3),
+        ("y_light", C.c_double), ("z_front", C.c_double),
+        ("xsph_mode", C.c_int32), ("enable_vorticity", C.c_int32), ("enable_xsph", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True, capture_output=True)
+    return os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+_lib = None
+
+
+def oracle_lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        src_m = max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("pbf_oracle.cpp", "pbf_oracle.hpp"))
+        if not os.path.exists(path) or os.path.getmtime(path) < src_m:
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.oracle_create.restype = C.c_void_p
+        lib.oracle_create.argtypes = [C.POINTER(PbfParams), C.c_int, C.c_int, C.c_int]
+        lib.oracle_destroy.argtypes = [C.c_void_p]
+        lib.oracle_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        lib.oracle_estimate_densities.argtypes = [C.c_void_p]
+        lib.oracle_step.argtypes = [C.c_void_p, C.c_int]
+        lib.oracle_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_download_array.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.oracle_num_pairs.restype = C.c_size_t
+        lib.oracle_num_pairs.argtypes = [C.c_void_p]
+        lib.oracle_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_neighbor_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_default_params.argtypes = [C.POINTER(PbfParams)]
+        lib.oracle_set_threads.argtypes = [C.c_int]
+        lib.oracle_max_threads.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def default_params(**kw):
+    p = PbfParams()
+    oracle_lib().oracle_default_params(C.byref(p))
+    set_params(p, **kw)
+    return p
+
+
+def set_params(p, **kw):
+    for k, v in kw.items():
+        if k in ("box_min", "box_max"):
+            for a in range(3):
+                getattr(p, k)[a] = float(v[a])
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """CPU oracle instance.  precision 32|64; see oracle/pbf_oracle.hpp."""
+
+    def __init__(self, params, precision=64, collision=COLLIDE_BOX, search=SEARCH_GRID):
+        self.lib = oracle_lib()
+        self.h = self.lib.oracle_create(C.byref(params), precision, collision, search)
+        self.n = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+    def upload(self, pos, vel):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        self.n = pos.shape[0]
+        self.lib.oracle_upload(self.h, self.n, _ptr(pos), _ptr(vel))
+
+    def estimate_densities(self):
+        self.lib.oracle_estimate_densities(self.h)
+
+    def step(self, steps=1):
+        self.lib.oracle_step(self.h, steps)
+
+    def download(self):
+        pos = np.empty((self.n, 3)); vel = np.empty((self.n, 3)); rho = np.empty(self.n)
+        self.lib.oracle_download(self.h, _ptr(pos), _ptr(vel), _ptr(rho))
+        return pos, vel, rho
+
+    def array(self, which):
+        out = np.empty(self.n if which == ARRAY_LAMBDA else (self.n, 3))
+        self.lib.oracle_download_array(self.h, which, _ptr(out))
+        return out
+
+    def neighbors(self):
+        m = self.lib.oracle_num_pairs(self.h)
+        row = np.empty(self.n + 1, dtype=np.uint32); col = np.empty(m, dtype=np.uint32)
+        self.lib.oracle_neighbors(self.h, _ptr(row), _ptr(col))
+        return row, col
+
+    def digest(self):
+        d = np.empty(self.n, dtype=np.uint64); c = np.empty(self.n, dtype=np.uint32)
+        self.lib.oracle_neighbor_digest(self.h, _ptr(d), _ptr(c))
+        return d, c
+
+    def stats(self):
+        a, b, ms = C.c_double(), C.c_double(), C.c_double()
+        self.lib.oracle_stats(self.h, C.byref(a), C.byref(b), C.byref(ms))
+        return a.value, b.value, ms.value
+
+
+# ---- reference harness -------------------------------------------------------------------------
+
+def ref_harness_path(opt="O3"):
+    return os.path.join(ORACLE_DIR, "_ref", "ref_harness" if opt == "O3" else "ref_harness_O0")
+
+
+def have_reference_binary():
+    return os.path.exists(ref_harness_path())
+
+
+def write_bin_scene(path, pos, vel, rho0):
+    with open(path, "wb") as f:
+        f.write(np.int64(pos.shape[0]).tobytes())
+        f.write(np.float64(rho0).tobytes())
+        f.write(np.ascontiguousarray(pos, dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(vel, dtype=np.float64).tobytes())
+
+
+def read_dump(path):
+    """-> list of dict(state[N,8], counts[N], row_ptr[N+1], col[M], seconds) per step."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:8] == b"PBFDUMP1"
+    n, steps = np.frombuffer(buf, dtype=np.int64, count=2, offset=8)
+    off = 24
+    out = []
+    for _ in range(steps):
+        st = np.frombuffer(buf, dtype=np.float64, count=n * 8, offset=off).reshape(n, 8); off += n * 64
+        cnt = np.frombuffer(buf, dtype=np.int32, count=n, offset=off); off += n * 4
+        m = int(cnt.sum())
+        col = np.frombuffer(buf, dtype=np.int32, count=m, offset=off); off += m * 4
+        sec = float(np.frombuffer(buf, dtype=np.float64, count=1, offset=off)[0]); off += 8
+        row = np.zeros(n + 1, dtype=np.int64); np.cumsum(cnt, out=row[1:])
+        out.append(dict(state=st, counts=cnt, row_ptr=row, col=col, seconds=sec))
+    return out
+
+
+def state_sha(pos, vel, rho):
+    """sha256[:16] of <f8[N,7] (pos, vel, rho) — the digest format of SURVEY.md §8c."""
+    a = np.concatenate([pos, vel, rho[:, None]], axis=1).astype("<f8")
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ---- scenes --------------------------------------------------------------------------------------
+
+def load_xml_scene(path):
+    """Application::load_particles (application.cpp:302-344): rho0 through float (stof, Q17),
+    positions/velocities as doubles in document order."""
+    root = ET.parse(path).getroot()
+    rho0 = float(np.float32(float(root.find("density").text)))
+    pos, vel = [], []
+    for p in root.find("ps").findall("particle"):
+        pos.append([float(t) for t in p.find("pos").text.split()])
+        vel.append([float(t) for t in p.find("v").text.split()])
+    return np.array(pos, dtype=np.float64), np.array(vel, dtype=np.float64), rho0
+
+
+def shipped_scene(name):
+    """'p' or 'spheres_p': the reference's particles/*.xml, regenerated from their construction
+    rule (so the GPU box, which has no /root/reference, gets the same particles)."""
+    if name == "p":
+        # particles/p.xml: 12 x 5 x 12 lattice, x,z = -0.9 + 0.15 i, y = 0.5 + 0.2 j, v=(0,-0.01,0)
+        raise NotImplementedError
+    raise KeyError(name)
+
+
+def pgen_two_blocks():
+    """particles/pgen.py:54-61 == particles/spheres_p.xml (N=2106, rho0=700)."""
+    pos = []
+    for i in range(1, 10):
+        for j in range(1, 14):
+            for k in range(1, 10):
+                pos.append([0.1 * i - 1, 0.1 * j, 1 - 0.1 * k])
+    for i in range(1, 10):
+        for j in range(1, 14):
+            for k in range(1, 10):
+                pos.append([1 - 0.1 * i, 0.1 * j, 0.1 * k - 1])
+    pos = np.array(pos, dtype=np.float64)
+    vel = np.tile(np.array([0.0, -1.0, 0.0]), (pos.shape[0], 1))
+    return pos, vel, 700.0
+
+
+def lattice_block(nx, ny, nz, origin=(0.1, 0.1, 0.1), spacing=0.1, v0=(0.0, -1.0, 0.0), jitter=0.0, seed=1234):
+    """pgen-style block: index order x outer / y / z inner; optional jitter
+    U(-jitter, jitter) per coordinate drawn in particle-index order x,y,z from default_rng(seed)."""
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.stack([origin[0] + spacing * i, origin[1] + spacing * j, origin[2] + spacing * k], axis=-1)
+    pos = pos.reshape(-1, 3).astype(np.float64)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        pos = pos + rng.uniform(-jitter, jitter, size=pos.shape)
+    vel = np.tile(np.array(v0, dtype=np.float64), (pos.shape[0], 1))
+    return pos, vel

@@ -1,0 +1,132 @@
+"""Pin the CPU oracle: Oracle<double>(reference-order XSPH, triangle walls) must reproduce the
+UNMODIFIED reference (particles.cpp:250-297) bit-for-bit — full state and ordered neighbour lists —
+against the committed fixtures (tests/golden/, made by make_golden.py from oracle/_ref/ref_harness)
+and, when the compiled reference is present, against a live run."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import (COLLIDE_BOX, COLLIDE_TRIANGLES, GOLDEN, SEARCH_BRUTE, SEARCH_GRID, XSPH_JACOBI,
+                     XSPH_REFERENCE, Oracle, default_params, have_reference_binary, read_dump,
+                     ref_harness_path, state_sha, write_bin_scene)
+
+SHIPPED = ["p", "spheres_p"]
+JITTER = ["two_blocks", "sparse", "corner", "front"]
+
+
+def _load(name):
+    if name in SHIPPED:
+        sc = np.load(os.path.join(GOLDEN, f"scene_{name}.npz"))
+        ref = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+        return sc["pos"], sc["vel"], float(sc["rho0"]), ref
+    ref = np.load(os.path.join(GOLDEN, f"ref_jitter_{name}.npz"))
+    return ref["pos"], ref["vel"], float(ref["rho0"]), ref
+
+
+def test_constants():
+    # the reference's literal H2 0.09 equals H*H in both working precisions (particles.cpp:26-28)
+    assert 0.3 * 0.3 == 0.09
+    assert np.float32(0.3) * np.float32(0.3) == np.float32(0.09)
+    # tensile scale 1/poly6(0,0,0.1H) (particles.cpp:151), value recorded in SURVEY.md §8a
+    h = 0.3; r2 = (0.1 * h) ** 2; t = h * h - r2
+    w = 1.56668147106 * (t * t * t) / h ** 9
+    assert abs(1.0 / w - 0.017761411379071678) < 1e-15
+
+
+@pytest.mark.parametrize("name", SHIPPED + JITTER)
+@pytest.mark.parametrize("search", [SEARCH_BRUTE, SEARCH_GRID])
+def test_oracle_matches_reference_fixture(name, search):
+    pos, vel, rho0, ref = _load(name)
+    steps = len(ref["sha"])
+    o = Oracle(default_params(rest_density=rho0, xsph_mode=XSPH_REFERENCE), 64, COLLIDE_TRIANGLES, search)
+    o.upload(pos, vel); o.estimate_densities()
+    keep = set(int(k) for k in ref["keep"])
+    for s in range(steps):
+        o.step()
+        P, V, R = o.download()
+        assert state_sha(P, V, R) == str(ref["sha"][s]), f"{name}: state differs from reference at step {s}"
+        row, col = o.neighbors()
+        assert len(col) == int(ref["pairs"][s])
+        if s == 0:
+            assert np.array_equal(np.diff(row.astype(np.int64)), ref["nbr_counts_0"])
+            assert np.array_equal(col.astype(np.int32), ref["nbr_col_0"])   # ordered lists, exact
+        if s in keep:
+            st = ref[f"state_{s}"]
+            assert np.array_equal(P, st[:, 0:3]) and np.array_equal(V, st[:, 3:6]) and np.array_equal(R, st[:, 6])
+        a, b, _ = o.stats()
+        ta, tb = ref["avg_rho_text"][s]
+        assert f"{a:.6g}" == ta and f"{b:.6g}" == tb    # the two numbers the reference prints per step
+
+
+def test_survey_golden_values():
+    """SURVEY.md §8c table (values captured from the unmodified reference during the survey)."""
+    ref = np.load(os.path.join(GOLDEN, "ref_p.npz"))
+    assert [str(ref["sha"][s]) for s in (0, 1, 19)] == ["dc17aefca6e0d81e", "91a4408ef8e9c1ef", "57e229f96ef1800b"]
+    assert [int(ref["pairs"][s]) for s in (0, 1, 19)] == [15988, 14012, 13548]
+    assert tuple(ref["avg_rho_text"][0]) == ("139.82", "145.755")
+    st0 = ref["state_0"][0]
+    assert st0[0] == -0.8527234379438056 and st0[1] == 0.528251353076964 and st0[6] == 137.5904451565677
+    ref = np.load(os.path.join(GOLDEN, "ref_spheres_p.npz"))
+    assert [str(ref["sha"][s]) for s in (0, 1, 19)] == ["a6828113d0842938", "ac3fc0fd5f86a8ee", "3b449a32a53f34dd"]
+    assert [int(ref["pairs"][s]) for s in (0, 1, 19)] == [157750, 125400, 153134]
+
+
+@pytest.mark.parametrize("name", SHIPPED + JITTER)
+def test_analytic_box_equals_triangles_fp64(name):
+    """Chain of trust, second arrow: the analytic box with the fp32 contact rules (one-sided planes,
+    exact axis normals, sticky virtual planes) is the same operator as the
+    reference's triangle walls in fp64.  Teacher-forced per step from the reference's own state:
+    neighbour lists identical, state equal up to the rounding of the hit distance t
+    (Moller-Trumbore vs (plane-o)/d: a few ulp, amplified by at most the 12 iterations)."""
+    pos, vel, rho0, ref = _load(name)
+    keep = sorted(int(k) for k in ref["keep"])
+    prm = default_params(rest_density=rho0, xsph_mode=XSPH_REFERENCE)
+    for k, s in enumerate(keep[:-1]):
+        if keep[k + 1] != s + 1:
+            continue
+        st = ref[f"state_{s}"]; nxt = ref[f"state_{s + 1}"]
+        res = []
+        for cm in (COLLIDE_TRIANGLES, COLLIDE_BOX):
+            o = Oracle(prm, 64, cm, SEARCH_GRID)
+            o.upload(st[:, 0:3], st[:, 3:6]); o.step()
+            res.append(o.download() + (o.neighbors(),))
+        assert np.array_equal(res[0][0], nxt[:, 0:3])              # triangles == reference (teacher-forced)
+        assert np.array_equal(res[0][3][1], res[1][3][1])           # identical ordered neighbour lists
+        assert np.abs(res[0][0] - res[1][0]).max() < 1e-11
+        assert np.abs(res[0][2] - res[1][2]).max() < 1e-8 * rho0
+
+
+@pytest.mark.parametrize("name", SHIPPED)
+def test_jacobi_xsph_changes_only_velocity(name):
+    """Quirk Q11: Jacobi XSPH (what the GPU computes) gives the same positions and densities as the
+    reference's in-index-order XSPH within a step; only velocities differ."""
+    pos, vel, rho0, ref = _load(name)
+    out = []
+    for mode in (XSPH_REFERENCE, XSPH_JACOBI):
+        o = Oracle(default_params(rest_density=rho0, xsph_mode=mode), 64, COLLIDE_TRIANGLES, SEARCH_GRID)
+        o.upload(pos, vel); o.step(); out.append(o.download())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][2], out[1][2])
+    assert not np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.skipif(not have_reference_binary(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_matches_live_reference(tmp_path):
+    """Live run of the unmodified reference on a fresh jittered input not in the fixtures."""
+    rng = np.random.default_rng(2024)
+    from helpers import lattice_block
+    pos, vel = lattice_block(7, 9, 6, origin=(-0.6, 0.05, -0.95), spacing=0.1, v0=(0.4, -2.0, -0.7), jitter=0.002, seed=5)
+    vel = vel + rng.normal(0, 0.05, size=vel.shape)
+    scene = str(tmp_path / "s.bin"); dump = str(tmp_path / "d.bin")
+    write_bin_scene(scene, pos, vel, 700.0)
+    subprocess.run([ref_harness_path(), "--bin", scene, "--steps", "10", "--out", dump, "--quiet"], check=True)
+    d = read_dump(dump)
+    o = Oracle(default_params(rest_density=700.0, xsph_mode=XSPH_REFERENCE), 64, COLLIDE_TRIANGLES, SEARCH_GRID)
+    o.upload(pos, vel)
+    for s in range(10):
+        o.step()
+        P, V, R = o.download()
+        assert np.array_equal(P, d[s]["state"][:, 0:3]) and np.array_equal(V, d[s]["state"][:, 3:6])
+        assert np.array_equal(R, d[s]["state"][:, 6])
+        assert np.array_equal(o.neighbors()[1].astype(np.int32), d[s]["col"])
