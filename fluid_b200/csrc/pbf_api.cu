@@ -1,0 +1,423 @@
+// pbf_api.cu — C ABI (include/pbf_b200.h) over the CUDA solver.  No torch types, no CPU fallback:
+// without a CUDA device every entry point fails with PBF_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "pbf_internal.h"
+
+using namespace pbf;
+
+namespace {
+
+#define CK(h, call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      (h)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return PBF_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+int fail(pbf_handle* h, int code, const char* msg) { if (h) h->last_error = msg; return code; }
+
+template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+// Parameters in fp32, computed with plain IEEE float operations (this TU is host code compiled by
+// the host compiler without fast-math; no contraction is possible on constants folded here).
+int fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
+  if (!(p.h > 0) || !(p.dt > 0) || !(p.rest_density > 0) || p.iterations < 0 || p.n_corr < 0) { err = "invalid PbfParams"; return PBF_ERR_INVALID; }
+  if (p.xsph_mode != PBF_XSPH_JACOBI) { err = "the GPU path implements PBF_XSPH_JACOBI only (SURVEY.md 7.3-3)"; return PBF_ERR_INVALID; }
+  volatile float h = (float)p.h;
+  d.h = h; d.h2 = h * h; d.dt = (float)p.dt; d.inv_dt = 1.0f / d.dt;
+  d.rho0 = (float)p.rest_density; d.inv_rho0 = 1.0f / d.rho0;
+  d.eps_relax = (float)p.eps_relax; d.kcorr = (float)p.k_corr; d.visc_c = (float)p.visc_c;
+  d.vort_dt_eps = d.dt * (float)p.vort_eps;
+  d.gdt = (float)(-p.gravity_y) * d.dt;            // velocity.y -= 10 * delta_t
+  d.eps_d = 1e-11f;
+  const double hd = (double)(float)p.h;
+  d.poly6_c = (float)(1.56668147106 / std::pow(hd, 9));
+  d.spiky_c = (float)(-3.0 * 4.774648292756860 / std::pow(hd, 6));
+  const double dq = p.dq_ratio * hd, t = hd * hd - dq * dq;
+  const double wdq = 1.56668147106 * t * t * t / std::pow(hd, 9);          // poly6(0,0,dq)
+  d.tscale_c = (float)((1.56668147106 / std::pow(hd, 9)) / wdq);
+  d.n_corr = p.n_corr; d.iterations = p.iterations;
+  d.enable_vorticity = p.enable_vorticity; d.enable_xsph = p.enable_xsph;
+  const float cell = d.h * (1.0f + 1.0f / 256.0f);
+  d.inv_cell = 1.0f / cell;
+  double ncell = 1;
+  for (int a = 0; a < 3; a++) {
+    if (!(p.box_max[a] > p.box_min[a])) { err = "empty box"; return PBF_ERR_INVALID; }
+    d.bmin[a] = (float)p.box_min[a]; d.bmax[a] = (float)p.box_max[a];
+    volatile float lo = d.bmin[a] + d.eps_d, hi = d.bmax[a] - d.eps_d;
+    d.clo[a] = lo; d.chi[a] = hi;
+    d.gmin[a] = d.bmin[a];
+    d.gdim[a] = (int)std::floor((p.box_max[a] - p.box_min[a]) / (double)cell) + 1;
+    ncell *= d.gdim[a];
+  }
+  d.yl = (float)p.y_light; d.zf = (float)p.z_front;
+  if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
+  return PBF_OK;
+}
+
+void free_arrays(pbf_handle* h) {
+  for (int b = 0; b < 2; b++) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->orig[b]); h->pos[b] = h->vel[b] = nullptr; h->orig[b] = nullptr; }
+  cudaFree(h->xs_tmp); cudaFree(h->xs_a); cudaFree(h->xs_b); cudaFree(h->vtmp); cudaFree(h->omega); cudaFree(h->xpred);
+  cudaFree(h->rho); cudaFree(h->cell_of); cudaFree(h->rank); cudaFree(h->perm); cudaFree(h->key);
+  cudaFree(h->nbr); cudaFree(h->slice_off); cudaFree(h->nbr_cnt); cudaFree(h->io_stage);
+  h->xs_tmp = h->xs_a = h->xs_b = h->vtmp = h->omega = h->xpred = nullptr; h->rho = nullptr;
+  h->cell_of = h->rank = h->perm = h->key = h->nbr = h->slice_off = h->nbr_cnt = nullptr; h->io_stage = nullptr;
+  h->cap = 0; h->nbr_cap_rows = 0;
+}
+
+int ensure_capacity(pbf_handle* h, size_t n) {
+  if (n <= h->cap) return PBF_OK;
+  free_arrays(h);
+  const size_t cap = (n + 31) / 32 * 32;
+  for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
+  CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
+  CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap));
+  CK(h, dmalloc(&h->cell_of, cap)); CK(h, dmalloc(&h->rank, cap)); CK(h, dmalloc(&h->perm, cap)); CK(h, dmalloc(&h->key, cap));
+  CK(h, dmalloc(&h->slice_off, cap / 32 + 1)); CK(h, dmalloc(&h->nbr_cnt, cap));
+  CK(h, dmalloc(&h->io_stage, cap * 7));
+  // neighbour rows: one row = 32 entries (one per lane of a slice).  Default 192 rows per slice
+  // (lattice spacing h/3 has 122 neighbours); PBF_NBR_ROWS overrides.  Overflow is an error.
+  size_t rows_per_slice = 192;
+  if (const char* e = getenv("PBF_NBR_ROWS")) rows_per_slice = (size_t)std::max(8, atoi(e));
+  h->nbr_cap_rows = (cap / 32) * rows_per_slice;
+  CK(h, dmalloc(&h->nbr, h->nbr_cap_rows * 32));
+  h->cap = cap;
+  return PBF_OK;
+}
+
+// double <-> float conversion of big host arrays, spread over a few host threads
+template <class F> void parallel_for(size_t n, F fn) {
+  unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  if (n < (1u << 16)) nt = 1;
+  if (nt == 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; t++) { size_t a = t * chunk, b = std::min(n, a + chunk); if (a < b) th.emplace_back(fn, a, b); }
+  for (auto& t : th) t.join();
+}
+
+struct PinnedBuf {
+  float* p = nullptr; size_t cap = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, n * sizeof(float));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+};
+
+int check_device_errors(pbf_handle* h) {
+  Scalars s;
+  CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+  if (s.err) {
+    int zero = 0;
+    cudaMemcpy(&h->sc->err, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    if (s.err & ERRBIT_NONFINITE) return fail(h, PBF_ERR_DOMAIN, "non-finite particle position produced by the step");
+    if (s.err & ERRBIT_MIGRATION) return fail(h, PBF_ERR_DOMAIN, "particle left its slab by more than one cell column in one step");
+    if (s.err & ERRBIT_NBR_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "neighbour list capacity exceeded (raise PBF_NBR_ROWS); results of this step are invalid");
+    if (s.err & ERRBIT_HALO_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "halo / migration buffer capacity exceeded");
+    return fail(h, PBF_ERR_CUDA, "unknown device error flag");
+  }
+  return PBF_OK;
+}
+
+}  // namespace
+
+// pinned staging lives outside the struct so pbf_internal.h stays CUDA-only
+struct HandleExtra { PinnedBuf pin; };
+static HandleExtra* extra_of(pbf_handle* h);
+
+#include <map>
+#include <mutex>
+static std::map<pbf_handle*, HandleExtra*> g_extra;
+static std::mutex g_extra_mu;
+static HandleExtra* extra_of(pbf_handle* h) {
+  std::lock_guard<std::mutex> g(g_extra_mu);
+  auto it = g_extra.find(h);
+  if (it != g_extra.end()) return it->second;
+  return g_extra[h] = new HandleExtra();
+}
+
+extern "C" {
+
+void pbf_default_params(PbfParams* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->h = 0.3; p->dt = 0.016; p->rest_density = 1000.0; p->eps_relax = 2.0; p->k_corr = 0.0001;
+  p->dq_ratio = 0.1; p->visc_c = 0.001; p->vort_eps = 0.001; p->gravity_y = -10.0;
+  p->n_corr = 4; p->iterations = 12;
+  p->box_min[0] = -1; p->box_min[1] = 0; p->box_min[2] = -1;
+  p->box_max[0] = 1; p->box_max[1] = 1.49; p->box_max[2] = 1;
+  p->y_light = 1.49; p->z_front = 1.0;
+  p->xsph_mode = PBF_XSPH_JACOBI; p->enable_vorticity = 1; p->enable_xsph = 1;
+}
+
+int pbf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int pbf_create(const PbfParams* params, int device_id, pbf_handle** out) {
+  if (!params || !out) return PBF_ERR_INVALID;
+  *out = nullptr;
+  const int ndev = pbf_device_count();
+  if (ndev <= 0) return PBF_ERR_NO_DEVICE;
+  if (device_id < 0 || device_id >= ndev) return PBF_ERR_INVALID;
+  pbf_handle* h = new pbf_handle();
+  h->device = device_id; h->hp = *params;
+  std::string err;
+  int rc = fill_dev_params(*params, h->dp, err);
+  if (rc != PBF_OK) { fprintf(stderr, "pbf_create: %s\n", err.c_str()); delete h; return rc; }
+  h->ncell = (uint32_t)((size_t)h->dp.gdim[0] * h->dp.gdim[1] * h->dp.gdim[2]);
+  auto bail = [&](cudaError_t e) { fprintf(stderr, "pbf_create: %s\n", cudaGetErrorString(e)); delete h; return PBF_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+  if ((e = dmalloc(&h->cell_count, (size_t)h->ncell + 1)) != cudaSuccess) return bail(e);
+  if ((e = dmalloc(&h->cell_start, (size_t)h->ncell + 2)) != cudaSuccess) return bail(e);
+  if ((e = dmalloc(&h->block_sums, (size_t)h->ncell / 2048 + 2)) != cudaSuccess) return bail(e);
+  if ((e = dmalloc(&h->sc, 1)) != cudaSuccess) return bail(e);
+  if ((e = cudaMemset(h->sc, 0, sizeof(Scalars))) != cudaSuccess) return bail(e);
+  cudaEventCreate(&h->ev_call[0]); cudaEventCreate(&h->ev_call[1]);
+  *out = h;
+  return PBF_OK;
+}
+
+void pbf_destroy(pbf_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->prof_collect();
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  free_arrays(h);
+  cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->block_sums); cudaFree(h->sc);
+  if (h->ev_call[0]) cudaEventDestroy(h->ev_call[0]);
+  if (h->ev_call[1]) cudaEventDestroy(h->ev_call[1]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  {
+    std::lock_guard<std::mutex> g(g_extra_mu);
+    auto it = g_extra.find(h);
+    if (it != g_extra.end()) { delete it->second; g_extra.erase(it); }
+  }
+  delete h;
+}
+
+const char* pbf_last_error(pbf_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+size_t pbf_num_particles(pbf_handle* h) { return h ? h->n : 0; }
+uint64_t pbf_launch_count(pbf_handle* h) { return h ? h->launches : 0; }
+
+int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz) {
+  if (!h || (n && (!pos_xyz || !vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload: null argument");
+  if (n > 0xFFFFFFF0ull) return fail(h, PBF_ERR_INVALID, "pbf_upload: more than 2^32 particles");
+  CK(h, cudaSetDevice(h->device));
+  int rc = ensure_capacity(h, n);
+  if (rc != PBF_OK) return rc;
+  h->n = n; h->cur = 0; h->have_neighbors = false;
+  if (n == 0) return PBF_OK;
+  HandleExtra* x = extra_of(h);
+  CK(h, x->pin.ensure(6 * n));
+  float* st = x->pin.p;
+  parallel_for(3 * n, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) { st[i] = (float)pos_xyz[i]; st[3 * n + i] = (float)vel_xyz[i]; }
+  });
+  CK(h, cudaMemcpyAsync(h->io_stage, st, 6 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  enqueue_import(h, h->io_stage, h->io_stage + 3 * n);
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaGetLastError());
+  return PBF_OK;
+}
+
+int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz) {
+  if (!h || (n && (!d_pos_xyz || !d_vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload_device: null argument");
+  CK(h, cudaSetDevice(h->device));
+  int rc = ensure_capacity(h, n);
+  if (rc != PBF_OK) return rc;
+  h->n = n; h->cur = 0; h->have_neighbors = false;
+  enqueue_import(h, d_pos_xyz, d_vel_xyz);
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaGetLastError());
+  return PBF_OK;
+}
+
+int pbf_step(pbf_handle* h, int n_steps) {
+  if (!h || n_steps < 0) return fail(h, PBF_ERR_INVALID, "pbf_step: bad argument");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaEventRecord(h->ev_call[0], h->stream));
+  for (int s = 0; s < n_steps; s++) enqueue_step(h);
+  CK(h, cudaEventRecord(h->ev_call[1], h->stream));
+  h->call_timed = true;
+  if (n_steps > 0 && h->n > 0) h->have_neighbors = true;
+  CK(h, cudaGetLastError());
+  return PBF_OK;
+}
+
+int pbf_sync(pbf_handle* h) {
+  if (!h) return PBF_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaGetLastError());
+  if (h->call_timed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]); h->last_call_ms = ms; h->call_timed = false; }
+  h->prof_collect();
+  return check_device_errors(h);
+}
+
+int pbf_estimate_densities(pbf_handle* h) {
+  if (!h) return PBF_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  enqueue_estimate_densities(h);
+  if (h->n > 0) h->have_neighbors = true;
+  return pbf_sync(h);
+}
+
+int pbf_stats(pbf_handle* h, double* first, double* final_, double* last_call_ms) {
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  Scalars s;
+  CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+  const double n = h->n ? (double)h->n : 1.0;
+  if (first) *first = s.rho_first / n;
+  if (final_) *final_ = s.rho_final / n;
+  if (last_call_ms) *last_call_ms = h->last_call_ms;
+  return PBF_OK;
+}
+
+int pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, float* d_density) {
+  if (!h) return PBF_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  if (d_pos_xyz) enqueue_export3(h, h->pos[h->cur], d_pos_xyz);
+  if (d_vel_xyz) enqueue_export3(h, h->vel[h->cur], d_vel_xyz);
+  if (d_density) enqueue_export1(h, h->rho, d_density);
+  return pbf_sync(h);
+}
+
+int pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density) {
+  if (!h) return PBF_ERR_INVALID;
+  const size_t n = h->n;
+  if (n == 0) return pbf_sync(h);
+  CK(h, cudaSetDevice(h->device));
+  HandleExtra* x = extra_of(h);
+  CK(h, x->pin.ensure(7 * n));
+  float* st = x->pin.p;
+  float* d = h->io_stage;
+  if (pos_xyz) { enqueue_export3(h, h->pos[h->cur], d); CK(h, cudaMemcpyAsync(st, d, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  if (vel_xyz) { enqueue_export3(h, h->vel[h->cur], d + 3 * n); CK(h, cudaMemcpyAsync(st + 3 * n, d + 3 * n, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  if (density) { enqueue_export1(h, h->rho, d + 6 * n); CK(h, cudaMemcpyAsync(st + 6 * n, d + 6 * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  parallel_for(3 * n, [&](size_t a, size_t b) {
+    if (pos_xyz) for (size_t i = a; i < b; i++) pos_xyz[i] = (double)st[i];
+    if (vel_xyz) for (size_t i = a; i < b; i++) vel_xyz[i] = (double)st[3 * n + i];
+  });
+  if (density) parallel_for(n, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) density[i] = (double)st[6 * n + i]; });
+  return PBF_OK;
+}
+
+// ---- parity / debug ---------------------------------------------------------------------------
+int pbf_debug_capture(pbf_handle* h, int on) {
+  if (!h) return PBF_ERR_INVALID;
+  h->capture_xpred = on ? 1 : 0;
+  if (on && !h->xpred && h->cap) CK(h, dmalloc(&h->xpred, h->cap));
+  return PBF_OK;
+}
+
+int pbf_debug_neighbor_digest(pbf_handle* h, uint64_t* digest, uint32_t* count) {
+  if (!h || !digest || !count) return PBF_ERR_INVALID;
+  if (!h->have_neighbors) return fail(h, PBF_ERR_INVALID, "no neighbour lists yet: call pbf_step first");
+  const size_t n = h->n;
+  CK(h, cudaSetDevice(h->device));
+  unsigned long long* dd = nullptr; uint32_t* dc = nullptr;
+  CK(h, dmalloc(&dd, n)); CK(h, dmalloc(&dc, n));
+  enqueue_digest(h, dd, dc);
+  int rc = pbf_sync(h);
+  if (rc == PBF_OK) {
+    cudaMemcpy(digest, dd, n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(count, dc, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dd); cudaFree(dc);
+  return rc;
+}
+
+int pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr, uint32_t* col_idx, size_t col_cap) {
+  if (!h || !row_ptr) return PBF_ERR_INVALID;
+  if (!h->have_neighbors) return fail(h, PBF_ERR_INVALID, "no neighbour lists yet: call pbf_step first");
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  const size_t n = h->n;
+  Scalars s;
+  CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> cnt(n), off(n / 32 + 1), orig(n), nb((size_t)s.nbr_cursor * 32);
+  CK(h, cudaMemcpy(cnt.data(), h->nbr_cnt, n * 4, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(off.data(), h->slice_off, (n / 32 + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(orig.data(), h->orig[h->cur], n * 4, cudaMemcpyDeviceToHost));
+  if (!nb.empty()) CK(h, cudaMemcpy(nb.data(), h->nbr, nb.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> count_orig(n);
+  for (size_t i = 0; i < n; i++) count_orig[orig[i]] = cnt[i];
+  row_ptr[0] = 0;
+  for (size_t i = 0; i < n; i++) row_ptr[i + 1] = row_ptr[i] + count_orig[i];
+  if (!col_idx) return PBF_OK;
+  if (row_ptr[n] > col_cap) return fail(h, PBF_ERR_CAPACITY, "col_idx too small");
+  for (size_t i = 0; i < n; i++) {
+    uint32_t* dst = col_idx + row_ptr[orig[i]];
+    const size_t base = (size_t)off[i / 32] * 32 + (i % 32);
+    for (uint32_t k = 0; k < cnt[i]; k++) dst[k] = orig[nb[base + (size_t)k * 32]];
+    std::sort(dst, dst + cnt[i]);
+  }
+  return PBF_OK;
+}
+
+int pbf_debug_download_array(pbf_handle* h, int which, double* out) {
+  if (!h || !out) return PBF_ERR_INVALID;
+  const size_t n = h->n;
+  if (n == 0) return PBF_OK;
+  CK(h, cudaSetDevice(h->device));
+  float* d = h->io_stage;
+  size_t m = 3 * n;
+  switch (which) {
+    case PBF_ARRAY_XSTAR: enqueue_export3(h, h->xs_a, d); break;
+    case PBF_ARRAY_LAMBDA: enqueue_export_w(h, h->xs_b, d); m = n; break;
+    case PBF_ARRAY_VORTICITY: enqueue_export3(h, h->omega, d); break;
+    case PBF_ARRAY_XPRED:
+      if (!h->capture_xpred || !h->xpred) return fail(h, PBF_ERR_INVALID, "call pbf_debug_capture(h,1) before the step");
+      enqueue_export3(h, h->xpred, d); break;
+    default: return fail(h, PBF_ERR_INVALID, "unknown array id");
+  }
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  std::vector<float> tmp(m);
+  CK(h, cudaMemcpy(tmp.data(), d, m * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < m; i++) out[i] = (double)tmp[i];
+  return PBF_OK;
+}
+
+int pbf_profile_enable(pbf_handle* h, int on) {
+  if (!h) return PBF_ERR_INVALID;
+  int rc = pbf_sync(h);
+  h->profiling = on != 0;
+  for (int k = 0; k < K_COUNT; k++) { h->prof_ms[k] = 0; h->prof_launches[k] = 0; }
+  return rc;
+}
+
+int pbf_profile_get(pbf_handle* h, int max, const char** names, double* total_ms, uint64_t* launches) {
+  if (!h) return 0;
+  pbf_sync(h);
+  int k = 0;
+  for (; k < K_COUNT && k < max; k++) {
+    if (names) names[k] = kKernelNames[k];
+    if (total_ms) total_ms[k] = h->prof_ms[k];
+    if (launches) launches[k] = h->prof_launches[k];
+  }
+  return k;
+}
+
+}  // extern "C"

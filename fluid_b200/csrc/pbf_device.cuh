@@ -1,0 +1,154 @@
+// pbf_device.cuh — device-side math of the B200 PBF step (sm_100a, fp32).
+//
+// Two arithmetic regimes live here, on purpose:
+//   * EXACT regime (predict + box collision + neighbour predicate): every operation is a single
+//     IEEE round-to-nearest fp32 op written with __f*_rn intrinsics, which nvcc never contracts
+//     into FMAs.  The result is bit-identical to the same expression compiled for the host with
+//     -ffp-contract=off, which is how the fp32 oracle is built, so predicted positions x* and the
+//     frozen neighbour SETS can be compared without tolerance.
+//   * FAST regime (lambda, delta-p, XSPH/vorticity sums): FMA contraction, rsqrtf, coefficients
+//     hoisted out of the pair loop.  Checked against the oracle with stated tolerances.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pbf {
+
+// Parameters in working precision; filled on the host (pbf_api.cu) in plain IEEE float arithmetic.
+struct DevParams {
+  float h, h2, dt, inv_dt, rho0, inv_rho0, eps_relax, kcorr, visc_c, vort_dt_eps, gdt, eps_d;
+  float poly6_c;      // 1.56668147106 / h^9
+  float spiky_c;      // -3 * 4.774648292756860 / h^6
+  float tscale_c;     // poly6_c * tensile scale: (W * tscale) == tscale_c * (h2-r2)^3
+  int   n_corr, iterations, enable_vorticity, enable_xsph;
+  float bmin[3], bmax[3];     // collision box
+  float clo[3], chi[3];       // hard clamp bounds: bmin + eps_d, bmax - eps_d
+  float yl, zf;               // virtual planes
+  // uniform grid (cell edge slightly larger than h => 27-cell search is conservative)
+  float inv_cell; float gmin[3];
+  int   gdim[3];              // cells per axis; linear id = (cx*gdim[1] + cy)*gdim[2] + cz  (z fastest)
+};
+
+// ---- EXACT regime -------------------------------------------------------------------------------
+__device__ __forceinline__ float ex_norm2(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// Frozen-neighbour predicate of the reference: (x_i - x_j).norm2() <= H2 (particles.cpp:260).
+__device__ __forceinline__ bool ex_is_neighbor(float3 a, float3 b, float h2) {
+  float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+  return ex_norm2(dx, dy, dz) <= h2;
+}
+
+__device__ __forceinline__ float comp(const float3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// One-sided analytic walls x-, x+, y-, z- (the Cornell box of particles.cpp:59-83 has an open
+// front and a light plane instead of z+ / y+ walls).  Same visiting order and "t <= max_t"
+// acceptance as the oracle's box_hit().
+__device__ __forceinline__ bool ex_box_hit(const DevParams& P, float3 o, float3 d, float& max_t,
+                                           int& axis, int& side, int skip_axis, int skip_side) {
+  bool hit = false;
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const int a = (w < 2) ? 0 : (w == 2 ? 1 : 2);
+    const int s = (w == 1) ? 1 : 0;
+    if (a == skip_axis && s == skip_side) continue;
+    const float plane = s ? P.bmax[a] : P.bmin[a];
+    const float da = comp(d, a);
+    if (s ? (da > 0.f) : (da < 0.f)) {
+      float t = __fdiv_rn(__fsub_rn(plane, comp(o, a)), da);
+      if (t < 0.f) t = 0.f;
+      if (t <= max_t) { max_t = t; hit = true; axis = a; side = s; }
+    }
+  }
+  return hit;
+}
+
+// Swept move of p by delta against the box: clamp() (respond=false, particles.cpp:51-84) and
+// clamp_response() (respond=true: slide once along the wall, particles.cpp:87-132), with the
+// fp32 contact rules of SURVEY.md §7.3-4 (one-sided planes, exact axis normals, sticky virtual
+// planes).  Mirrors Oracle<float>::collide(COLLIDE_ANALYTIC_BOX) operation for operation.
+__device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float3 delta, bool respond) {
+  const float total_l = __fsqrt_rn(ex_norm2(delta.x, delta.y, delta.z));
+  float l = total_l;
+  if (!(l <= P.eps_d)) {
+    const float rc = __fdiv_rn(1.f, l);
+    float3 d = make_float3(__fmul_rn(rc, delta.x), __fmul_rn(rc, delta.y), __fmul_rn(rc, delta.z));
+    bool virt = false;
+    if (d.z > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.zf, p.z), d.z); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
+    if (d.y > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.yl, p.y), d.y); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
+    float max_t = l; int axis = -1, side = 0;
+    const bool hit = ex_box_hit(P, p, d, max_t, axis, side, -1, 0);
+    if (hit || virt) {
+      const float s = __fsub_rn(max_t, P.eps_d);
+      p.x = __fadd_rn(p.x, __fmul_rn(s, d.x));
+      p.y = __fadd_rn(p.y, __fmul_rn(s, d.y));
+      p.z = __fadd_rn(p.z, __fmul_rn(s, d.z));
+      if (respond && hit && !virt) {
+        const float dn = side ? -comp(d, axis) : comp(d, axis);
+        float3 tg = delta;
+        if (axis == 0) tg.x = 0.f; else if (axis == 1) tg.y = 0.f; else tg.z = 0.f;
+        const float t2 = ex_norm2(tg.x, tg.y, tg.z);
+        if (dn > -1.f && t2 > 0.f) {
+          const float rn = __fdiv_rn(1.f, __fsqrt_rn(t2));
+          float3 d2 = make_float3(__fmul_rn(rn, tg.x), __fmul_rn(rn, tg.y), __fmul_rn(rn, tg.z));
+          float mt = __fmul_rn(__fsub_rn(total_l, max_t), 0.5f);
+          int a2 = -1, s2 = 0;
+          ex_box_hit(P, p, d2, mt, a2, s2, axis, side);
+          const float s3 = __fsub_rn(mt, P.eps_d);
+          p.x = __fadd_rn(p.x, __fmul_rn(s3, d2.x));
+          p.y = __fadd_rn(p.y, __fmul_rn(s3, d2.y));
+          p.z = __fadd_rn(p.z, __fmul_rn(s3, d2.z));
+        }
+      }
+    } else {
+      p.x = __fadd_rn(p.x, delta.x); p.y = __fadd_rn(p.y, delta.y); p.z = __fadd_rn(p.z, delta.z);
+    }
+    // hard clamp, std::min/std::max semantics of particles.cpp:81-83
+    float t;
+    t = (p.x < P.chi[0]) ? p.x : P.chi[0]; p.x = (P.clo[0] < t) ? t : P.clo[0];
+    t = (p.y < P.chi[1]) ? p.y : P.chi[1]; p.y = (P.clo[1] < t) ? t : P.clo[1];
+    t = (p.z < P.chi[2]) ? p.z : P.chi[2]; p.z = (P.clo[2] < t) ? t : P.clo[2];
+  }
+  return p;
+}
+
+// Cell coordinates of a position (clamped into the grid).  Conservative for the 27-cell search
+// because the cell edge is h*(1+2^-8) and fp32 rounding of (x-gmin)*inv_cell is << 2^-9 cells
+// for the domains we support (<= 2^12 cells per axis).
+__device__ __forceinline__ int3 cell_coords(const DevParams& P, float x, float y, float z) {
+  int cx = (int)floorf((x - P.gmin[0]) * P.inv_cell);
+  int cy = (int)floorf((y - P.gmin[1]) * P.inv_cell);
+  int cz = (int)floorf((z - P.gmin[2]) * P.inv_cell);
+  cx = min(max(cx, 0), P.gdim[0] - 1);
+  cy = min(max(cy, 0), P.gdim[1] - 1);
+  cz = min(max(cz, 0), P.gdim[2] - 1);
+  return make_int3(cx, cy, cz);
+}
+__device__ __forceinline__ uint32_t cell_linear(const DevParams& P, int3 c) {
+  return (uint32_t)((c.x * P.gdim[1] + c.y) * P.gdim[2] + c.z);
+}
+
+// ---- FAST regime: pair terms -------------------------------------------------------------------
+// For r = x_i - x_j returns (via refs) the un-scaled poly6 term t^3 (t = h2 - r2, 0 outside the
+// support; particles.cpp:134-141) and the un-scaled spiky gradient magnitude g such that
+// grad W = spiky_c * g * r_vec, g = (h - r)^2 / r (0 for r >= h or r < 1e-11; particles.cpp:143-149).
+__device__ __forceinline__ void pair_terms(const DevParams& P, float dx, float dy, float dz,
+                                           float& r2, float& w3, float& g) {
+  r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float t = P.h2 - r2;
+  w3 = (r2 < P.h2) ? t * t * t : 0.f;
+  const float rinv = rsqrtf(r2);
+  const float r = r2 * rinv;
+  const float hr = P.h - r;
+  g = (r < P.h && r2 >= 1e-22f) ? hr * hr * rinv : 0.f;
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t j) {   // == pbf_oracle::mix64
+  uint64_t z = j + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace pbf

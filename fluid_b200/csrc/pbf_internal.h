@@ -1,0 +1,95 @@
+// pbf_internal.h — solver state shared by pbf_kernels.cu (device code) and pbf_api.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pbf_b200.h"
+#include "pbf_device.cuh"
+
+namespace pbf {
+
+enum { ERRBIT_NBR_CAPACITY = 1, ERRBIT_NONFINITE = 2, ERRBIT_HALO_CAPACITY = 4, ERRBIT_MIGRATION = 8 };
+
+// device-resident scalars (one allocation)
+struct Scalars {
+  unsigned long long nbr_cursor;   // rows (of 32 entries) handed out by the neighbour build
+  int err; int pad;
+  double rho_first, rho_final;     // sum of densities: first lambda pass / finalize pass
+  unsigned int counters[8];        // slab packing cursors
+};
+
+enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
+                K_VELOCITY, K_VORT_XSPH, K_CONFINE, K_DENSITY, K_IO, K_SLAB, K_COUNT };
+static const char* const kKernelNames[K_COUNT] = {
+  "predict_collide_hash", "cell_scan", "scatter", "cell_sort", "reorder", "build_neighbors", "lambda",
+  "delta_collide", "velocity", "vorticity_xsph", "confine_commit", "density_only", "io", "slab"};
+
+struct Solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  PbfParams hp;
+  DevParams dp;
+  std::string last_error;
+
+  size_t n = 0, cap = 0;
+  uint32_t ncell = 0;
+  int cur = 0;                       // which of the double-buffered pos/vel/orig holds the state
+  float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
+  uint32_t* orig[2] = {nullptr, nullptr};
+  float4 *xs_tmp = nullptr, *xs_a = nullptr, *xs_b = nullptr, *vtmp = nullptr, *omega = nullptr, *xpred = nullptr;
+  float* rho = nullptr;
+  uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr, *key = nullptr;
+  uint32_t *cell_count = nullptr, *cell_start = nullptr, *block_sums = nullptr;
+  uint32_t *nbr = nullptr, *slice_off = nullptr, *nbr_cnt = nullptr;
+  size_t nbr_cap_rows = 0;           // capacity of nbr in rows of 32 entries
+  Scalars* sc = nullptr;             // device
+  float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
+  int capture_xpred = 0;
+  bool have_neighbors = false;
+
+  uint64_t launches = 0, steps_done = 0;
+  double last_call_ms = 0.0;
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
+  bool call_timed = false;
+
+  // optional per-kernel profiling with CUDA events on the launching stream
+  bool profiling = false;
+  struct ProfRec { int kid; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[K_COUNT] = {0};
+  uint64_t prof_launches[K_COUNT] = {0};
+  cudaEvent_t prof_pending = nullptr;
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_begin(int) { if (profiling) { prof_pending = get_event(); cudaEventRecord(prof_pending, stream); } }
+  void prof_end(int kid) {
+    if (profiling) { cudaEvent_t b = get_event(); cudaEventRecord(b, stream); prof_recs.push_back({kid, prof_pending, b}); }
+  }
+  void prof_collect() {   // call after a stream sync
+    for (auto& r : prof_recs) {
+      float ms = 0.f; cudaEventElapsedTime(&ms, r.a, r.b);
+      prof_ms[r.kid] += ms; prof_launches[r.kid]++;
+      event_pool.push_back(r.a); event_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+  }
+};
+
+void enqueue_step(Solver* h);
+void enqueue_estimate_densities(Solver* h);
+void sort_and_build(Solver* h, int apply_forces, int include_self);
+void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz);
+void enqueue_export3(Solver* h, const float4* src, float* dst_xyz);
+void enqueue_export1(Solver* h, const float* src, float* dst);
+void enqueue_export_w(Solver* h, const float4* src, float* dst);
+void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count);
+
+}  // namespace pbf
+
+struct pbf_handle : public pbf::Solver {};

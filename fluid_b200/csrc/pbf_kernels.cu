@@ -1,0 +1,544 @@
+// pbf_kernels.cu — hand-written sm_100a kernels of the PBF step and their launch sequence.
+//
+// Replaces Particles::timeStep (reference src/particles.cpp:250-297).  Pass structure:
+//   predict+collide+hash -> counting sort by cell (hist / scan / scatter / canonical in-cell order /
+//   reorder to cell-sorted float4 SoA) -> frozen neighbour lists (SELL-32, built once per step from
+//   the predicted positions, like the reference's all-pairs loop 258-265) -> I x (lambda, delta-p +
+//   collide) -> velocity, vorticity + XSPH + density -> confinement + commit.
+// No tensor cores: this is a gather-bound stencil, not a contraction.
+#include "pbf_internal.h"
+
+namespace pbf {
+
+static constexpr int TPB = 256;          // threads per block for per-particle kernels
+static constexpr int SCAN_ITEMS = 8;     // items per thread in the cell scan
+static constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x, v.y, v.z); }
+
+// ------------------------------------------------------------------------------------------------
+// A. predict + collide + hash      (applyForceVelocity + clamp_response, particles.cpp:175-183,87-132)
+// EXACT regime: x* is bit-identical to the fp32 oracle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_predict_hash(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ pos,
+               float4* __restrict__ vel, float4* __restrict__ xs_tmp, uint32_t* __restrict__ cell_of,
+               uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count, int apply_forces,
+               Scalars* __restrict__ sc) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const float4 x = pos[i];
+  float3 p = xyz(x);
+  if (apply_forces) {
+    float4 v = vel[i];
+    v.y = __fsub_rn(v.y, P.gdt);                                   // velocity.y -= 10 * delta_t
+    const float3 delta = make_float3(__fmul_rn(v.x, P.dt), __fmul_rn(v.y, P.dt), __fmul_rn(v.z, P.dt));
+    p = ex_collide(P, p, delta, true);
+    vel[i] = v;                                                    // clamp_response leaves v untouched (Q9)
+  }
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { atomicOr(&sc->err, ERRBIT_NONFINITE); p = make_float3(P.clo[0], P.clo[1], P.clo[2]); }
+  xs_tmp[i] = make_float4(p.x, p.y, p.z, 0.f);
+  const uint32_t c = cell_linear(P, cell_coords(P, p.x, p.y, p.z));
+  cell_of[i] = c;
+  rank[i] = atomicAdd(&cell_count[c], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// B. exclusive scan of the cell histogram -> cell_start[0..ncell]   (3 launches)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& block_total) {
+  __shared__ uint32_t warp_sums[TPB / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = (lane < TPB / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < TPB / 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+    if (lane < TPB / 32) warp_sums[lane] = ws;   // inclusive over warps
+  }
+  __syncthreads();
+  const uint32_t warp_off = wid ? warp_sums[wid - 1] : 0u;
+  block_total = warp_sums[TPB / 32 - 1];
+  __syncthreads();
+  return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_scan_reduce(uint32_t ncell, const uint32_t* __restrict__ count, uint32_t* __restrict__ block_sums) {
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < ncell) s += count[base + k];
+  uint32_t total;
+  block_exclusive_scan(s, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_scan_block_sums(uint32_t nblocks, uint32_t* __restrict__ block_sums) {
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < nblocks; base += TPB) {
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t v = idx < nblocks ? block_sums[idx] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, total);
+    if (idx < nblocks) block_sums[idx] = running + ex;
+    running += total;
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_scan_apply(uint32_t ncell, const uint32_t* __restrict__ count, const uint32_t* __restrict__ block_sums,
+             uint32_t* __restrict__ cell_start) {
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS]; uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < ncell) ? count[base + k] : 0u; s += v[k]; }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(s, total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < ncell) cell_start[base + k] = off; off += v[k]; }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == TPB - 1) cell_start[ncell] = off;   // == n
+}
+
+// ------------------------------------------------------------------------------------------------
+// C. scatter to cell order, canonical order inside each cell (ascending original id), reorder
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_scatter(uint32_t n, const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank,
+          const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ orig,
+          uint32_t* __restrict__ perm, uint32_t* __restrict__ key) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = cell_start[cell_of[i]] + rank[i];
+  perm[slot] = i;
+  key[slot] = orig[i];
+}
+
+// The atomic rank above is arrival order, i.e. not reproducible.  Sorting each cell's few particles
+// by their original id makes the whole layout (and therefore every floating-point sum downstream)
+// a pure function of the particle state: runs are bit-reproducible, and a slab decomposition sees
+// the same order as one GPU does.
+__global__ void __launch_bounds__(TPB)
+k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ perm,
+            uint32_t* __restrict__ key) {
+  const uint32_t c = blockIdx.x * TPB + threadIdx.x;
+  if (c >= ncell) return;
+  const uint32_t s = cell_start[c], e = cell_start[c + 1];
+  for (uint32_t a = s + 1; a < e; a++) {
+    const uint32_t k = key[a], p = perm[a];
+    uint32_t b = a;
+    while (b > s && key[b - 1] > k) { key[b] = key[b - 1]; perm[b] = perm[b - 1]; b--; }
+    key[b] = k; perm[b] = p;
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_reorder(uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
+          const float4* __restrict__ pos_in, const float4* __restrict__ vel_in, const float4* __restrict__ xs_tmp,
+          float4* __restrict__ pos_out, float4* __restrict__ vel_out, float4* __restrict__ xs_out,
+          uint32_t* __restrict__ orig_out) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t i = perm[s];
+  pos_out[s] = pos_in[i];
+  vel_out[s] = vel_in[i];
+  xs_out[s] = xs_tmp[i];
+  orig_out[s] = key[s];
+}
+
+// ------------------------------------------------------------------------------------------------
+// D. frozen neighbour lists  (all-pairs loop particles.cpp:258-265 -> 27-cell search, EXACT predicate)
+// Layout SELL-32: the 32 particles of a warp form a slice; entry s of lane l lives at
+// nbr[(slice_off + s)*32 + l], so every later pass reads its indices fully coalesced.
+// Two passes over the 9 z-runs of candidates (count, then fill) — no truncation, ever.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ nbr,
+                  uint32_t* __restrict__ slice_off, uint32_t* __restrict__ nbr_cnt,
+                  unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < n;
+  float3 pi = make_float3(0.f, 0.f, 0.f);
+  uint32_t jb[9], je[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { jb[k] = 0; je[k] = 0; }
+  if (valid) {
+    pi = xyz(xs[i]);
+    const int3 c = cell_coords(P, pi.x, pi.y, pi.z);
+    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, P.gdim[2] - 1);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const int cx = c.x + (k / 3) - 1, cy = c.y + (k % 3) - 1;
+      if (cx >= 0 && cx < P.gdim[0] && cy >= 0 && cy < P.gdim[1]) {
+        const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
+        jb[k] = cell_start[base + zlo];
+        je[k] = cell_start[base + zhi + 1];
+      }
+    }
+  }
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 9; k++)
+    for (uint32_t j = jb[k]; j < je[k]; j++) {
+      const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
+      cnt += take ? 1u : 0u;
+    }
+  const uint32_t m = __reduce_max_sync(0xffffffffu, cnt);
+  unsigned long long off = 0;
+  if (lane == 0) {
+    off = atomicAdd(&sc->nbr_cursor, (unsigned long long)m);
+    if (off + m > cap_rows) { atomicOr(&sc->err, ERRBIT_NBR_CAPACITY); off = ~0ull; }
+  }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (!valid) return;
+  if (off == ~0ull) { nbr_cnt[i] = 0; if (lane == 0) slice_off[i >> 5] = 0; return; }
+  if (lane == 0) slice_off[i >> 5] = (uint32_t)off;
+  nbr_cnt[i] = cnt;
+  uint32_t* out = nbr + off * 32ull + lane;
+#pragma unroll
+  for (int k = 0; k < 9; k++)
+    for (uint32_t j = jb[k]; j < je[k]; j++) {
+      const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
+      if (take) { *out = j; out += 32; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E. solver iteration: lambda pass (newtonStepCalculateLambda, particles.cpp:185-204)
+//    reads xs_in.xyz, writes xs_out = (xyz unchanged, w = lambda_i)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_to_double(float v, double* target) {
+  // warp shuffle reduce, one double atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(target, (double)v);
+  return v;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs_in,
+         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
+         const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  float rho = 0.f;
+  if (i < n) {
+    const float4 pi = xs_in[i];
+    const uint32_t cnt = nbr_cnt[i];
+    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+    float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
+#pragma unroll 4
+    for (uint32_t s = 0; s < cnt; s++) {
+      const uint32_t j = lst[(size_t)s * 32u];
+      const float4 pj = __ldg(&xs_in[j]);
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      float r2, w3, g;
+      pair_terms(P, dx, dy, dz, r2, w3, g);
+      w3s += w3;
+      gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz);
+      dsum = fmaf(g * g, r2, dsum);
+    }
+    rho = P.poly6_c * w3s;
+    const float gs = P.spiky_c * P.inv_rho0;            // grad_j C_i = gs * g * r_vec
+    const float Gx = gs * gx, Gy = gs * gy, Gz = gs * gz;
+    const float denom = gs * gs * dsum + (Gx * Gx + Gy * Gy + Gz * Gz);
+    const float c_i = rho * P.inv_rho0 - 1.f;            // not clamped at 0 (Q7)
+    const float lambda = -c_i / (denom + P.eps_relax);
+    xs_out[i] = make_float4(pi.x, pi.y, pi.z, lambda);
+    if (rho_out) rho_out[i] = rho;
+  }
+  if (rho_sum) block_sum_to_double(rho, rho_sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// F. solver iteration: delta-p + collide (newtonStepUpdatePosition + clamp, particles.cpp:206-213,51-84)
+//    reads xs_in = (x*, lambda), writes xs_out.xyz = corrected position
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_delta(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs_in,
+        float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
+        const uint32_t* __restrict__ nbr_cnt) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const float4 pi = xs_in[i];
+  const uint32_t cnt = nbr_cnt[i];
+  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+  float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll 4
+  for (uint32_t s = 0; s < cnt; s++) {
+    const uint32_t j = lst[(size_t)s * 32u];
+    const float4 pj = __ldg(&xs_in[j]);
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    float r2, w3, g;
+    pair_terms(P, dx, dy, dz, r2, w3, g);
+    float q = P.tscale_c * w3;                           // W / W(dq)
+    float qn = q;
+    for (int e = 1; e < P.n_corr; e++) qn *= q;
+    if (P.n_corr == 0) qn = 1.f;
+    const float f = (pi.w + pj.w - P.kcorr * qn) * g;     // (lambda_i + lambda_j + s_corr) * |grad|/r
+    ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
+  }
+  const float sc = P.spiky_c * P.inv_rho0;
+  const float3 dp = make_float3(sc * ax, sc * ay, sc * az);
+  const float3 p = ex_collide(P, make_float3(pi.x, pi.y, pi.z), dp, false);
+  xs_out[i] = make_float4(p.x, p.y, p.z, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// G. finalize: velocity update (215-217), vorticity + XSPH + density (219-234, Jacobi, §7.3-3),
+//    confinement + commit (236-248)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+           const float4* __restrict__ pos, float4* __restrict__ vtmp) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = xs[i], b = pos[i];
+  vtmp[i] = make_float4(P.inv_dt * (a.x - b.x), P.inv_dt * (a.y - b.y), P.inv_dt * (a.z - b.z), 0.f);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+                 const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
+                 float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
+                 const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
+                 double* __restrict__ rho_sum) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  float rho = 0.f;
+  if (i < n) {
+    const float4 pi = xs[i];
+    const float4 vi = vtmp[i];
+    const uint32_t cnt = nbr_cnt[i];
+    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+    float w3s = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 2
+    for (uint32_t s = 0; s < cnt; s++) {
+      const uint32_t j = lst[(size_t)s * 32u];
+      const float4 pj = __ldg(&xs[j]);
+      const float4 vj = __ldg(&vtmp[j]);
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;   // v_ij = v_j - v_i
+      float r2, w3, g;
+      pair_terms(P, dx, dy, dz, r2, w3, g);
+      // omega += v_ij x grad W   (grad W = spiky_c * g * d)
+      ox = fmaf(g, uy * dz - uz * dy, ox);
+      oy = fmaf(g, uz * dx - ux * dz, oy);
+      oz = fmaf(g, ux * dy - uy * dx, oz);
+      sx = fmaf(w3, ux, sx); sy = fmaf(w3, uy, sy); sz = fmaf(w3, uz, sz);
+      w3s += w3;
+    }
+    rho = P.poly6_c * w3s;
+    ox *= P.spiky_c; oy *= P.spiky_c; oz *= P.spiky_c;
+    omega[i] = make_float4(ox, oy, oz, sqrtf(ox * ox + oy * oy + oz * oz));
+    const float xc = P.enable_xsph ? P.visc_c * P.poly6_c : 0.f;   // v += C * sum v_ij W  (not density-normalised, Q12)
+    vel_out[i] = make_float4(fmaf(xc, sx, vi.x), fmaf(xc, sy, vi.y), fmaf(xc, sz, vi.z), 0.f);
+    rho_out[i] = rho;                                              // the density the visualiser reads
+  }
+  if (rho_sum) block_sum_to_double(rho, rho_sum);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_confine_commit(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+                 const float4* __restrict__ omega, float4* __restrict__ vel, float4* __restrict__ pos,
+                 const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
+                 const uint32_t* __restrict__ nbr_cnt) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const float4 pi = xs[i];
+  if (P.enable_vorticity) {
+    const uint32_t cnt = nbr_cnt[i];
+    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+#pragma unroll 2
+    for (uint32_t s = 0; s < cnt; s++) {
+      const uint32_t j = lst[(size_t)s * 32u];
+      const float4 pj = __ldg(&xs[j]);
+      const float wn = __ldg(&omega[j].w);
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      float r2, w3, g;
+      pair_terms(P, dx, dy, dz, r2, w3, g);
+      const float f = wn * g;                            // |omega_j| * grad W (no own term, Q13)
+      ex = fmaf(f, dx, ex); ey = fmaf(f, dy, ey); ez = fmaf(f, dz, ez);
+    }
+    ex *= P.spiky_c; ey *= P.spiky_c; ez *= P.spiky_c;
+    const float en = sqrtf(ex * ex + ey * ey + ez * ez);
+    if (en > P.eps_d) {
+      const float rn = 1.f / en;
+      const float nx = rn * ex, ny = rn * ey, nz = rn * ez;
+      const float4 w = omega[i];
+      float4 v = vel[i];
+      v.x = fmaf(P.vort_dt_eps, ny * w.z - nz * w.y, v.x);
+      v.y = fmaf(P.vort_dt_eps, nz * w.x - nx * w.z, v.y);
+      v.z = fmaf(P.vort_dt_eps, nx * w.y - ny * w.x, v.z);
+      vel[i] = v;
+    }
+  }
+  pos[i] = make_float4(pi.x, pi.y, pi.z, 0.f);            // updatePosition (246-248)
+}
+
+// load-time density: sum of poly6 over the frozen set INCLUDING self (particles.cpp:158-163,440-444)
+__global__ void __launch_bounds__(TPB)
+k_density_only(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+               float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
+               const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const float4 pi = xs[i];
+  const uint32_t cnt = nbr_cnt[i];
+  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+  float w3s = 0.f;
+  for (uint32_t s = 0; s < cnt; s++) {
+    const float4 pj = __ldg(&xs[lst[(size_t)s * 32u]]);
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    float r2, w3, g;
+    pair_terms(P, dx, dy, dz, r2, w3, g);
+    w3s += w3;
+  }
+  rho_out[i] = P.poly6_c * w3s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H. I/O helpers: original order <-> sorted order, fp32 AoS xyz <-> float4 SoA
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_import(uint32_t n, const float* __restrict__ pos_xyz, const float* __restrict__ vel_xyz,
+         float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ orig) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  pos[i] = make_float4(pos_xyz[3 * i], pos_xyz[3 * i + 1], pos_xyz[3 * i + 2], 0.f);
+  vel[i] = make_float4(vel_xyz[3 * i], vel_xyz[3 * i + 1], vel_xyz[3 * i + 2], 0.f);
+  orig[i] = i;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_export3(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst_xyz) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  const float4 v = src[s];
+  const size_t o = orig[s];
+  dst_xyz[3 * o] = v.x; dst_xyz[3 * o + 1] = v.y; dst_xyz[3 * o + 2] = v.z;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_export1(uint32_t n, const float* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  dst[orig[s]] = src[s];
+}
+
+__global__ void __launch_bounds__(TPB)
+k_export_w(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  dst[orig[s]] = src[s].w;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_neighbor_digest(uint32_t n, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
+                  const uint32_t* __restrict__ nbr_cnt, const uint32_t* __restrict__ orig,
+                  unsigned long long* __restrict__ digest, uint32_t* __restrict__ count) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t cnt = nbr_cnt[i];
+  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+  unsigned long long d = 0;
+  for (uint32_t s = 0; s < cnt; s++) d += mix64((uint64_t)orig[lst[(size_t)s * 32u]]);
+  digest[orig[i]] = d;
+  count[orig[i]] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch sequence
+// ------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(size_t n, int per_block = TPB) { return (unsigned)((n + per_block - 1) / per_block); }
+
+#define LAUNCH(h, kid, kern, grid, ...)                                   \
+  do {                                                                    \
+    (h)->prof_begin(kid);                                                 \
+    kern<<<(grid), TPB, 0, (h)->stream>>>(__VA_ARGS__);                   \
+    (h)->prof_end(kid);                                                   \
+    (h)->launches++;                                                      \
+  } while (0)
+
+// Sort the particles of pos/vel buffers `cur` by the cell of their predicted position (or of their
+// committed position when apply_forces == 0), leaving cell-sorted pos/vel/orig in buffers cur^1
+// and x* in xs_a; then build the frozen neighbour lists on xs_a.
+void sort_and_build(Solver* h, int apply_forces, int include_self) {
+  const uint32_t n = (uint32_t)h->n;
+  const uint32_t ncell = h->ncell;
+  const int cur = h->cur, nxt = cur ^ 1;
+  cudaMemsetAsync(h->cell_count, 0, sizeof(uint32_t) * ncell, h->stream);
+  cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
+  LAUNCH(h, K_PREDICT, k_predict_hash, blocks_for(n), h->dp, n, h->pos[cur], h->vel[cur], h->xs_tmp, h->cell_of,
+         h->rank, h->cell_count, apply_forces, h->sc);
+  const unsigned sb = blocks_for(ncell, SCAN_TILE);
+  LAUNCH(h, K_SCAN, k_scan_reduce, sb, ncell, h->cell_count, h->block_sums);
+  LAUNCH(h, K_SCAN, k_scan_block_sums, 1, sb, h->block_sums);
+  LAUNCH(h, K_SCAN, k_scan_apply, sb, ncell, h->cell_count, h->block_sums, h->cell_start);
+  LAUNCH(h, K_SCATTER, k_scatter, blocks_for(n), n, h->cell_of, h->rank, h->cell_start, h->orig[cur], h->perm, h->key);
+  LAUNCH(h, K_CELLSORT, k_cell_sort, blocks_for(ncell), ncell, h->cell_start, h->perm, h->key);
+  LAUNCH(h, K_REORDER, k_reorder, blocks_for(n), n, h->perm, h->key, h->pos[cur], h->vel[cur], h->xs_tmp,
+         h->pos[nxt], h->vel[nxt], h->xs_a, h->orig[nxt]);
+  h->cur = nxt;
+  LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(n), h->dp, n, h->xs_a, h->cell_start, h->nbr, h->slice_off,
+         h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
+}
+
+void enqueue_step(Solver* h) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n == 0) return;
+  const unsigned g = blocks_for(n);
+  cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);   // rho_first, rho_final
+  sort_and_build(h, 1, 0);
+  const int cur = h->cur;
+  if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
+  for (int it = 0; it < h->dp.iterations; it++) {
+    LAUNCH(h, K_LAMBDA, k_lambda, g, h->dp, n, h->xs_a, h->xs_b, h->nbr, h->slice_off, h->nbr_cnt,
+           (float*)nullptr, it == 0 ? &h->sc->rho_first : (double*)nullptr);
+    LAUNCH(h, K_DELTA, k_delta, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+  }
+  LAUNCH(h, K_VELOCITY, k_velocity, g, h->dp, n, h->xs_a, h->pos[cur], h->vtmp);
+  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, g, h->dp, n, h->xs_a, h->vtmp, h->vel[cur], h->omega, h->rho, h->nbr,
+         h->slice_off, h->nbr_cnt, &h->sc->rho_final);
+  LAUNCH(h, K_CONFINE, k_confine_commit, g, h->dp, n, h->xs_a, h->omega, h->vel[cur], h->pos[cur], h->nbr,
+         h->slice_off, h->nbr_cnt);
+  h->steps_done++;
+}
+
+void enqueue_estimate_densities(Solver* h) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n == 0) return;
+  sort_and_build(h, 0, 1);
+  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt);
+}
+
+void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n == 0) return;
+  LAUNCH(h, K_IO, k_import, blocks_for(n), n, d_pos_xyz, d_vel_xyz, h->pos[h->cur], h->vel[h->cur], h->orig[h->cur]);
+}
+
+void enqueue_export3(Solver* h, const float4* src, float* dst_xyz) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n) LAUNCH(h, K_IO, k_export3, blocks_for(n), n, src, h->orig[h->cur], dst_xyz);
+}
+void enqueue_export1(Solver* h, const float* src, float* dst) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n) LAUNCH(h, K_IO, k_export1, blocks_for(n), n, src, h->orig[h->cur], dst);
+}
+void enqueue_export_w(Solver* h, const float4* src, float* dst) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n) LAUNCH(h, K_IO, k_export_w, blocks_for(n), n, src, h->orig[h->cur], dst);
+}
+void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n) LAUNCH(h, K_IO, k_neighbor_digest, blocks_for(n), n, h->nbr, h->slice_off, h->nbr_cnt, h->orig[h->cur], digest, count);
+}
+
+}  // namespace pbf

@@ -102,6 +102,8 @@ int  pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr /*n+1*/, uint
 enum { PBF_ARRAY_XSTAR = 0 /*n*3 predicted/corrected positions*/, PBF_ARRAY_LAMBDA = 1 /*n*/,
        PBF_ARRAY_VORTICITY = 2 /*n*3*/, PBF_ARRAY_XPRED = 3 /*n*3 x* right after predict+collide*/ };
 int  pbf_debug_download_array(pbf_handle* h, int which, double* out);
+/* Keep a copy of x* right after predict+collide (PBF_ARRAY_XPRED) during subsequent steps. */
+int  pbf_debug_capture(pbf_handle* h, int on);
 /* Number of kernel launches issued by this handle so far (bench "gpu_launches"). */
 uint64_t pbf_launch_count(pbf_handle* h);
 /* Per-kernel device time (CUDA events) accumulated since the last reset; names are static.

@@ -1,0 +1,41 @@
+"""Quick per-kernel timing of the step on a pgen-style dam-break block (dev tool, not bench.py)."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from fluid_b200 import api
+
+def block(nx, ny, nz, jitter=0.001):
+    i, j, k = np.meshgrid(np.arange(nx, dtype=np.float32), np.arange(ny, dtype=np.float32), np.arange(nz, dtype=np.float32), indexing="ij")
+    pos = np.stack([0.1 + 0.1 * i, 0.1 + 0.1 * j, 0.1 + 0.1 * k], axis=-1).reshape(-1, 3).astype(np.float64)
+    if jitter:
+        pos += np.random.default_rng(1234).uniform(-jitter, jitter, size=pos.shape)
+    vel = np.tile(np.array([0.0, -1.0, 0.0]), (pos.shape[0], 1))
+    return pos, vel
+
+def main():
+    nx, ny, nz = (int(a) for a in sys.argv[1:4])
+    steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    iters = int(sys.argv[5]) if len(sys.argv) > 5 else 12
+    box_max = (max(30.0, 0.3 * nx), max(15.0, 0.15 * ny), 0.1 * nz + 0.1)
+    p = api.default_params(rest_density=700.0, iterations=iters, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
+    s = api.Solver(p)
+    pos, vel = block(nx, ny, nz)
+    n = pos.shape[0]
+    t0 = time.time(); s.upload(pos, vel); t_up = time.time() - t0
+    s.step(2)   # warm-up
+    s.profile_enable(True)
+    s.step(steps)
+    a, b, ms = s.stats()
+    prof = s.profile()
+    s.profile_enable(False)
+    s.step(steps)
+    a, b, ms2 = s.stats()
+    d, c = s.neighbor_digest()
+    t0 = time.time(); P, V, R = s.download(); t_down = time.time() - t0
+    out = dict(n=n, iters=iters, steps=steps, ms_per_step_profiled=ms / steps, ms_per_step=ms2 / steps,
+               particle_iter_per_s=n * iters * steps / (ms2 * 1e-3), avg_rho=(a, b), mean_nbrs=float(c.mean()), max_nbrs=int(c.max()),
+               upload_s=t_up, download_s=t_down,
+               kernels={k: dict(ms_per_step=v[0] / steps, launches_per_step=v[1] / steps) for k, v in prof.items() if v[1]})
+    print(json.dumps(out, indent=1))
+
+main()
