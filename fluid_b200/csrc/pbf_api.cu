@@ -76,19 +76,21 @@ void free_arrays(pbf_handle* h) {
 int ensure_capacity(pbf_handle* h, size_t n) {
   if (n <= h->cap) return PBF_OK;
   free_arrays(h);
-  const size_t cap = (n + 31) / 32 * 32;
+  const size_t cap = (n + 1 + 31) / 32 * 32;   // +1: the sentinel particle lives at index n
   for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
   CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
   CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap));
   CK(h, dmalloc(&h->cell_of, cap)); CK(h, dmalloc(&h->rank, cap)); CK(h, dmalloc(&h->perm, cap)); CK(h, dmalloc(&h->key, cap));
   CK(h, dmalloc(&h->slice_off, cap / 32 + 1)); CK(h, dmalloc(&h->nbr_cnt, cap));
   CK(h, dmalloc(&h->io_stage, cap * 7));
-  // neighbour rows: one row = 32 entries (one per lane of a slice).  Default 192 rows per slice
-  // (lattice spacing h/3 has 122 neighbours); PBF_NBR_ROWS overrides.  Overflow is an error.
-  size_t rows_per_slice = 192;
-  if (const char* e = getenv("PBF_NBR_ROWS")) rows_per_slice = (size_t)std::max(8, atoi(e));
+  if (h->capture_xpred) CK(h, dmalloc(&h->xpred, cap));
+  // neighbour rows: one row = 32 uint4 = 4 entries per lane of a slice.  Default 48 rows per slice
+  // = room for 192 neighbours per particle (lattice spacing h/3 has 122); PBF_NBR_ROWS overrides.
+  // Overflow is an error, never a truncation.
+  size_t rows_per_slice = 48;
+  if (const char* e = getenv("PBF_NBR_ROWS")) rows_per_slice = (size_t)std::max(4, atoi(e));
   h->nbr_cap_rows = (cap / 32) * rows_per_slice;
-  CK(h, dmalloc(&h->nbr, h->nbr_cap_rows * 32));
+  CK(h, dmalloc(&h->nbr, h->nbr_cap_rows * 128));
   h->cap = cap;
   return PBF_OK;
 }
@@ -356,7 +358,7 @@ int pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr, uint32_t* col
   const size_t n = h->n;
   Scalars s;
   CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
-  std::vector<uint32_t> cnt(n), off(n / 32 + 1), orig(n), nb((size_t)s.nbr_cursor * 32);
+  std::vector<uint32_t> cnt(n), off(n / 32 + 1), orig(n), nb((size_t)s.nbr_cursor * 128);
   CK(h, cudaMemcpy(cnt.data(), h->nbr_cnt, n * 4, cudaMemcpyDeviceToHost));
   CK(h, cudaMemcpy(off.data(), h->slice_off, (n / 32 + 1) * 4, cudaMemcpyDeviceToHost));
   CK(h, cudaMemcpy(orig.data(), h->orig[h->cur], n * 4, cudaMemcpyDeviceToHost));
@@ -369,8 +371,8 @@ int pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr, uint32_t* col
   if (row_ptr[n] > col_cap) return fail(h, PBF_ERR_CAPACITY, "col_idx too small");
   for (size_t i = 0; i < n; i++) {
     uint32_t* dst = col_idx + row_ptr[orig[i]];
-    const size_t base = (size_t)off[i / 32] * 32 + (i % 32);
-    for (uint32_t k = 0; k < cnt[i]; k++) dst[k] = orig[nb[base + (size_t)k * 32]];
+    const size_t base = (size_t)off[i / 32] * 128 + (i % 32) * 4;
+    for (uint32_t k = 0; k < cnt[i]; k++) dst[k] = orig[nb[base + (size_t)(k >> 2) * 128 + (k & 3)]];
     std::sort(dst, dst + cnt[i]);
   }
   return PBF_OK;

@@ -130,18 +130,27 @@ __device__ __forceinline__ uint32_t cell_linear(const DevParams& P, int3 c) {
 }
 
 // ---- FAST regime: pair terms -------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_ftz(float x) {   // one MUFU.RSQ, no denormal fix-up code
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // For r = x_i - x_j returns (via refs) the un-scaled poly6 term t^3 (t = h2 - r2, 0 outside the
 // support; particles.cpp:134-141) and the un-scaled spiky gradient magnitude g such that
-// grad W = spiky_c * g * r_vec, g = (h - r)^2 / r (0 for r >= h or r < 1e-11; particles.cpp:143-149).
+// grad W = spiky_c * g * r_vec, g = (h - r)^2 / r (0 for r >= h; particles.cpp:143-149).
+// Branch-free: the cut-offs are max(.,0) clamps (ALU pipe) instead of compare+select.  The
+// reference's "r < 1e-11 -> 0" guard (coincident particles) becomes a clamp of r2 from below:
+// g stays finite and multiplies a zero r_vec, so the contribution is 0 as in the reference.
 __device__ __forceinline__ void pair_terms(const DevParams& P, float dx, float dy, float dz,
                                            float& r2, float& w3, float& g) {
   r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  const float t = P.h2 - r2;
-  w3 = (r2 < P.h2) ? t * t * t : 0.f;
-  const float rinv = rsqrtf(r2);
+  const float t = fmaxf(P.h2 - r2, 0.f);
+  w3 = t * t * t;
+  const float rinv = rsqrt_ftz(fmaxf(r2, 1e-22f));
   const float r = r2 * rinv;
-  const float hr = P.h - r;
-  g = (r < P.h && r2 >= 1e-22f) ? hr * hr * rinv : 0.f;
+  const float hr = fmaxf(P.h - r, 0.f);
+  g = hr * hr * rinv;
 }
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t j) {   // == pbf_oracle::mix64

@@ -153,9 +153,12 @@ k_reorder(uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restr
 
 // ------------------------------------------------------------------------------------------------
 // D. frozen neighbour lists  (all-pairs loop particles.cpp:258-265 -> 27-cell search, EXACT predicate)
-// Layout SELL-32: the 32 particles of a warp form a slice; entry s of lane l lives at
-// nbr[(slice_off + s)*32 + l], so every later pass reads its indices fully coalesced.
-// Two passes over the 9 z-runs of candidates (count, then fill) — no truncation, ever.
+// Layout SELL-32x4: the 32 particles of a warp form a slice; a row holds one uint4 (4 neighbour
+// indices) per lane, so entry s of lane l lives at nbr[(slice_off + s/4)*128 + 4*l + s%4] and
+// every later pass reads its indices as fully coalesced 16-byte loads.  Lists are padded to a
+// multiple of 4 with the sentinel index n (a particle parked far outside the domain, so it adds
+// exactly 0 to every sum).  Two passes over the 9 z-runs of candidates (count, then fill) — no
+// truncation, ever.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB)
 k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
@@ -190,7 +193,7 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4*
       const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
       cnt += take ? 1u : 0u;
     }
-  const uint32_t m = __reduce_max_sync(0xffffffffu, cnt);
+  const uint32_t m = (__reduce_max_sync(0xffffffffu, cnt) + 3u) >> 2;    // rows of uint4
   unsigned long long off = 0;
   if (lane == 0) {
     off = atomicAdd(&sc->nbr_cursor, (unsigned long long)m);
@@ -201,14 +204,41 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4*
   if (off == ~0ull) { nbr_cnt[i] = 0; if (lane == 0) slice_off[i >> 5] = 0; return; }
   if (lane == 0) slice_off[i >> 5] = (uint32_t)off;
   nbr_cnt[i] = cnt;
-  uint32_t* out = nbr + off * 32ull + lane;
+  uint32_t* out = nbr + off * 128ull + lane * 4;
+  uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < 9; k++)
     for (uint32_t j = jb[k]; j < je[k]; j++) {
       const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
-      if (take) { *out = j; out += 32; }
+      if (take) { out[(size_t)(s >> 2) * 128u + (s & 3u)] = j; s++; }
     }
+  for (; s & 3u; s++) out[(size_t)(s >> 2) * 128u + (s & 3u)] = n;       // sentinel padding
 }
+
+// the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
+__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* vtmp, float4* omega) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    a[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    b[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    vtmp[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    omega[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// Visit the frozen neighbours of the calling thread's particle: body(p_j float4, extra...) is
+// applied to 4 gathered neighbours per coalesced uint4 index load, with the next index row
+// prefetched while the current one is processed.
+#define PBF_FOR_NEIGHBORS(i, BODY)                                                                   \
+  {                                                                                                  \
+    const uint4* lst_ = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[(i) >> 5] * 32u + (threadIdx.x & 31); \
+    const uint32_t rows_ = (nbr_cnt[i] + 3u) >> 2;                                                   \
+    uint4 nx_ = rows_ ? __ldg(lst_) : make_uint4(0, 0, 0, 0);                                        \
+    for (uint32_t r_ = 0; r_ < rows_; r_++) {                                                        \
+      const uint4 jj_ = nx_;                                                                         \
+      if (r_ + 1 < rows_) nx_ = __ldg(lst_ + (size_t)(r_ + 1) * 32u);                                \
+      BODY(jj_.x) BODY(jj_.y) BODY(jj_.z) BODY(jj_.w)                                                \
+    }                                                                                                \
+  }
 
 // ------------------------------------------------------------------------------------------------
 // E. solver iteration: lambda pass (newtonStepCalculateLambda, particles.cpp:185-204)
@@ -230,20 +260,19 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restri
   float rho = 0.f;
   if (i < n) {
     const float4 pi = xs_in[i];
-    const uint32_t cnt = nbr_cnt[i];
-    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
     float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
-#pragma unroll 4
-    for (uint32_t s = 0; s < cnt; s++) {
-      const uint32_t j = lst[(size_t)s * 32u];
-      const float4 pj = __ldg(&xs_in[j]);
-      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      float r2, w3, g;
-      pair_terms(P, dx, dy, dz, r2, w3, g);
-      w3s += w3;
-      gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz);
-      dsum = fmaf(g * g, r2, dsum);
+#define BODY_L(J)                                                          \
+    {                                                                      \
+      const float4 pj = __ldg(&xs_in[J]);                                  \
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;    \
+      float r2, w3, g;                                                     \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                \
+      w3s += w3;                                                           \
+      gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz);    \
+      dsum = fmaf(g * g, r2, dsum);                                        \
     }
+    PBF_FOR_NEIGHBORS(i, BODY_L)
+#undef BODY_L
     rho = P.poly6_c * w3s;
     const float gs = P.spiky_c * P.inv_rho0;            // grad_j C_i = gs * g * r_vec
     const float Gx = gs * gx, Gy = gs * gy, Gz = gs * gz;
@@ -259,7 +288,9 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restri
 // ------------------------------------------------------------------------------------------------
 // F. solver iteration: delta-p + collide (newtonStepUpdatePosition + clamp, particles.cpp:206-213,51-84)
 //    reads xs_in = (x*, lambda), writes xs_out.xyz = corrected position
+//    NCORR: artificial-pressure exponent known at compile time (4 = reference), or -1 = runtime.
 // ------------------------------------------------------------------------------------------------
+template <int NCORR>
 __global__ void __launch_bounds__(TPB)
 k_delta(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
@@ -267,23 +298,22 @@ k_delta(const __grid_constant__ DevParams P, uint32_t n, const float4* __restric
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const float4 pi = xs_in[i];
-  const uint32_t cnt = nbr_cnt[i];
-  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
   float ax = 0.f, ay = 0.f, az = 0.f;
-#pragma unroll 4
-  for (uint32_t s = 0; s < cnt; s++) {
-    const uint32_t j = lst[(size_t)s * 32u];
-    const float4 pj = __ldg(&xs_in[j]);
-    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-    float r2, w3, g;
-    pair_terms(P, dx, dy, dz, r2, w3, g);
-    float q = P.tscale_c * w3;                           // W / W(dq)
-    float qn = q;
-    for (int e = 1; e < P.n_corr; e++) qn *= q;
-    if (P.n_corr == 0) qn = 1.f;
-    const float f = (pi.w + pj.w - P.kcorr * qn) * g;     // (lambda_i + lambda_j + s_corr) * |grad|/r
-    ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);
+#define BODY_D(J)                                                          \
+  {                                                                        \
+    const float4 pj = __ldg(&xs_in[J]);                                    \
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;      \
+    float r2, w3, g;                                                       \
+    pair_terms(P, dx, dy, dz, r2, w3, g);                                  \
+    const float q = P.tscale_c * w3;                 /* W / W(dq) */       \
+    float qn;                                                              \
+    if (NCORR == 4) { const float q2 = q * q; qn = q2 * q2; }              \
+    else { qn = 1.f; for (int e = 0; e < P.n_corr; e++) qn *= q; }         \
+    const float f = (pi.w + pj.w - P.kcorr * qn) * g;                      \
+    ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);      \
   }
+  PBF_FOR_NEIGHBORS(i, BODY_D)
+#undef BODY_D
   const float sc = P.spiky_c * P.inv_rho0;
   const float3 dp = make_float3(sc * ax, sc * ay, sc * az);
   const float3 p = ex_collide(P, make_float3(pi.x, pi.y, pi.z), dp, false);
@@ -314,25 +344,23 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t n, const float4* 
   if (i < n) {
     const float4 pi = xs[i];
     const float4 vi = vtmp[i];
-    const uint32_t cnt = nbr_cnt[i];
-    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
     float w3s = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll 2
-    for (uint32_t s = 0; s < cnt; s++) {
-      const uint32_t j = lst[(size_t)s * 32u];
-      const float4 pj = __ldg(&xs[j]);
-      const float4 vj = __ldg(&vtmp[j]);
-      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;   // v_ij = v_j - v_i
-      float r2, w3, g;
-      pair_terms(P, dx, dy, dz, r2, w3, g);
-      // omega += v_ij x grad W   (grad W = spiky_c * g * d)
-      ox = fmaf(g, uy * dz - uz * dy, ox);
-      oy = fmaf(g, uz * dx - ux * dz, oy);
-      oz = fmaf(g, ux * dy - uy * dx, oz);
-      sx = fmaf(w3, ux, sx); sy = fmaf(w3, uy, sy); sz = fmaf(w3, uz, sz);
-      w3s += w3;
+#define BODY_V(J)                                                                     \
+    {                                                                                 \
+      const float4 pj = __ldg(&xs[J]);                                                \
+      const float4 vj = __ldg(&vtmp[J]);                                              \
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;               \
+      const float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;               \
+      float r2, w3, g;                                                                \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                           \
+      ox = fmaf(g, uy * dz - uz * dy, ox);  /* omega += v_ij x grad W */              \
+      oy = fmaf(g, uz * dx - ux * dz, oy);                                            \
+      oz = fmaf(g, ux * dy - uy * dx, oz);                                            \
+      sx = fmaf(w3, ux, sx); sy = fmaf(w3, uy, sy); sz = fmaf(w3, uz, sz);            \
+      w3s += w3;                                                                      \
     }
+    PBF_FOR_NEIGHBORS(i, BODY_V)
+#undef BODY_V
     rho = P.poly6_c * w3s;
     ox *= P.spiky_c; oy *= P.spiky_c; oz *= P.spiky_c;
     omega[i] = make_float4(ox, oy, oz, sqrtf(ox * ox + oy * oy + oz * oz));
@@ -352,20 +380,19 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t n, const float4* 
   if (i >= n) return;
   const float4 pi = xs[i];
   if (P.enable_vorticity) {
-    const uint32_t cnt = nbr_cnt[i];
-    const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
     float ex = 0.f, ey = 0.f, ez = 0.f;
-#pragma unroll 2
-    for (uint32_t s = 0; s < cnt; s++) {
-      const uint32_t j = lst[(size_t)s * 32u];
-      const float4 pj = __ldg(&xs[j]);
-      const float wn = __ldg(&omega[j].w);
-      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      float r2, w3, g;
-      pair_terms(P, dx, dy, dz, r2, w3, g);
-      const float f = wn * g;                            // |omega_j| * grad W (no own term, Q13)
-      ex = fmaf(f, dx, ex); ey = fmaf(f, dy, ey); ez = fmaf(f, dz, ez);
+#define BODY_C(J)                                                          \
+    {                                                                      \
+      const float4 pj = __ldg(&xs[J]);                                     \
+      const float wn = __ldg(&omega[J].w);                                 \
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;    \
+      float r2, w3, g;                                                     \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                \
+      const float f = wn * g;      /* |omega_j| * grad W (no own term, Q13) */ \
+      ex = fmaf(f, dx, ex); ey = fmaf(f, dy, ey); ez = fmaf(f, dz, ez);    \
     }
+    PBF_FOR_NEIGHBORS(i, BODY_C)
+#undef BODY_C
     ex *= P.spiky_c; ey *= P.spiky_c; ez *= P.spiky_c;
     const float en = sqrtf(ex * ex + ey * ey + ez * ez);
     if (en > P.eps_d) {
@@ -390,16 +417,17 @@ k_density_only(const __grid_constant__ DevParams P, uint32_t n, const float4* __
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const float4 pi = xs[i];
-  const uint32_t cnt = nbr_cnt[i];
-  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
   float w3s = 0.f;
-  for (uint32_t s = 0; s < cnt; s++) {
-    const float4 pj = __ldg(&xs[lst[(size_t)s * 32u]]);
-    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-    float r2, w3, g;
-    pair_terms(P, dx, dy, dz, r2, w3, g);
-    w3s += w3;
+#define BODY_R(J)                                                          \
+  {                                                                        \
+    const float4 pj = __ldg(&xs[J]);                                       \
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;      \
+    float r2, w3, g;                                                       \
+    pair_terms(P, dx, dy, dz, r2, w3, g);                                  \
+    w3s += w3;                                                             \
   }
+  PBF_FOR_NEIGHBORS(i, BODY_R)
+#undef BODY_R
   rho_out[i] = P.poly6_c * w3s;
 }
 
@@ -446,9 +474,9 @@ k_neighbor_digest(uint32_t n, const uint32_t* __restrict__ nbr, const uint32_t* 
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const uint32_t cnt = nbr_cnt[i];
-  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 32u + (threadIdx.x & 31);
+  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 128u + (threadIdx.x & 31) * 4u;
   unsigned long long d = 0;
-  for (uint32_t s = 0; s < cnt; s++) d += mix64((uint64_t)orig[lst[(size_t)s * 32u]]);
+  for (uint32_t s = 0; s < cnt; s++) d += mix64((uint64_t)orig[lst[(size_t)(s >> 2) * 128u + (s & 3u)]]);
   digest[orig[i]] = d;
   count[orig[i]] = cnt;
 }
@@ -486,6 +514,9 @@ void sort_and_build(Solver* h, int apply_forces, int include_self) {
   LAUNCH(h, K_REORDER, k_reorder, blocks_for(n), n, h->perm, h->key, h->pos[cur], h->vel[cur], h->xs_tmp,
          h->pos[nxt], h->vel[nxt], h->xs_a, h->orig[nxt]);
   h->cur = nxt;
+  h->prof_begin(K_REORDER);
+  k_set_sentinel<<<1, 32, 0, h->stream>>>(n, h->xs_a, h->xs_b, h->vtmp, h->omega);
+  h->prof_end(K_REORDER); h->launches++;
   LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(n), h->dp, n, h->xs_a, h->cell_start, h->nbr, h->slice_off,
          h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
 }
@@ -501,7 +532,8 @@ void enqueue_step(Solver* h) {
   for (int it = 0; it < h->dp.iterations; it++) {
     LAUNCH(h, K_LAMBDA, k_lambda, g, h->dp, n, h->xs_a, h->xs_b, h->nbr, h->slice_off, h->nbr_cnt,
            (float*)nullptr, it == 0 ? &h->sc->rho_first : (double*)nullptr);
-    LAUNCH(h, K_DELTA, k_delta, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+    if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+    else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
   }
   LAUNCH(h, K_VELOCITY, k_velocity, g, h->dp, n, h->xs_a, h->pos[cur], h->vtmp);
   LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, g, h->dp, n, h->xs_a, h->vtmp, h->vel[cur], h->omega, h->rho, h->nbr,

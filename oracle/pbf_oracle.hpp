@@ -78,7 +78,7 @@ struct Oracle {
   PbfParams P;
   int collision_mode, search_mode;
   // parameters in working precision (particles.cpp:24-44)
-  R H, H2, DT, RHO0, EPS_RELAX, KCORR, VISC, VORT_EPS, GRAV, EPS_D, TSCALE;
+  R H, H2, H6, H9, DT, RHO0, EPS_RELAX, KCORR, VISC, VORT_EPS, GRAV, EPS_D, TSCALE;
   int NCORR, ITERS;
   V bmin, bmax; R YL, ZF;
   std::vector<Tri<R>> tris;
@@ -92,6 +92,7 @@ struct Oracle {
 
   Oracle(const PbfParams& p, int cmode, int smode) : P(p), collision_mode(cmode), search_mode(smode) {
     H = R(p.h); H2 = H * H;   // literal H2 0.09 == 0.3*0.3 in fp64 and fp32 (tests assert it)
+    H6 = intpow(H, 6); H9 = intpow(H, 9);   // intpow<6>(H), intpow<9>(H): hoisted, same bits
     DT = R(p.dt); RHO0 = R(p.rest_density); EPS_RELAX = R(p.eps_relax); KCORR = R(p.k_corr);
     VISC = R(p.visc_c); VORT_EPS = R(p.vort_eps); GRAV = R(p.gravity_y); EPS_D = R(1e-11);  // misc.h:11
     NCORR = p.n_corr; ITERS = p.iterations;
@@ -124,14 +125,14 @@ struct Oracle {
     R r2 = r.norm2();
     if (r2 >= H2) return R(0);
     R t = H2 - r2;
-    return R(1.56668147106) * intpow(t, 3) / intpow(H, 9);
+    return R(1.56668147106) * intpow(t, 3) / H9;
   }
   V grad_spiky(const V& r) const {
     R rl = r.norm();
     if (rl >= H || rl < EPS_D) return V();
     // -3 * 4.77... * intpow<2>(H - r_l) * r / (intpow<6>(H) * r_l)
     R s = R(-3 * 4.774648292756860) * intpow(H - rl, 2);
-    return (s * r) / (intpow(H, 6) * rl);
+    return (s * r) / (H6 * rl);
   }
 
   // ---- ray / triangle (static_scene/marching_triangle.cpp:21-73), segment [0, max_t] -----------

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (key roofline / stall metrics per captured kernel) or a launch-list csv.
+usage: ncu_summary.py prof.ncu-rep | launches.csv"""
+import collections, csv, io, subprocess, sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
+
+
+def rep(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("==", r[hdr.index("Kernel Name")].split("(")[0])
+        for k in KEYS:
+            if k in hdr:
+                print(f"  {k:72s} {r[hdr.index(k)]} {units[hdr.index(k)]}")
+        st = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
+                try:
+                    st.append((float(r[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+        print("  stalls (warps per issue):", ", ".join(f"{h}={v:.2f}" for v, h in sorted(st, reverse=True)[:6]))
+
+
+def launches(path):
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]; ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot = collections.defaultdict(float); cnt = collections.Counter()
+    for r in rows[1:]:
+        v = float(r[vi].replace(",", "")); u = r[ui]
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1.0)
+        name = r[ki].split("(")[0]; tot[name] += v; cnt[name] += 1
+    T = sum(tot.values())
+    for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+        print(f"{k:28s} {cnt[k]:4d} launches {v:10.3f} ms total {v / cnt[k]:9.4f} ms/launch {100 * v / T:5.1f}%")
+    print(f"total {T:.3f} ms over {sum(cnt.values())} launches")
+
+
+if __name__ == "__main__":
+    (rep if sys.argv[1].endswith(".ncu-rep") else launches)(sys.argv[1])

@@ -123,12 +123,12 @@ def test_single_pass_kernels(name):
         assert _rel(Vg, Vo) < 1e-5, f"{name}/{label}: velocity rel err {_rel(Vg, Vo):.2e}"
 
 
-def _gate_whole_step(tag, Pg, Rg, Po, Ro, rho0):
+def _gate_whole_step(tag, Pg, Rg, Po, Ro, rho0, p50_gate=1e-5):
     dx = np.linalg.norm(Pg - Po, axis=1)
     p50, p99, mx = np.percentile(dx, 50), np.percentile(dx, 99), dx.max()
     drho = np.abs(Rg - Ro) / rho0
     msg = f"{tag}: |dx| p50 {p50:.2e} p99 {p99:.2e} max {mx:.2e}; drho/rho0 p99 {np.percentile(drho, 99):.2e}; n>1e-3: {np.count_nonzero(dx > 1e-3)}"
-    assert p50 <= 1e-5 and p99 <= 5e-3 and mx <= 1e-1, msg
+    assert p50 <= p50_gate and p99 <= 5e-3 and mx <= 1e-1, msg
     assert np.percentile(drho, 99) <= 1e-2, msg
     return msg
 
@@ -200,23 +200,32 @@ def test_deterministic():
 
 
 def test_rollout_drift_vs_fp64_oracle():
-    """100 free-running steps: per-particle comparison is meaningless after a few steps (chaos,
-    SURVEY.md §7.3-5); aggregates must stay close."""
+    """Free-running rollouts: per-particle comparison is meaningless after a few steps (chaos,
+    SURVEY.md §7.3-5); aggregates must stay close.  Gates calibrated with the two CPU oracles
+    against each other on this 2106-particle sloshing scene (fp32 vs fp64, same algorithm):
+    kinetic energy agrees to 1 % at step 25 but only to 30-70 % at steps 50-100 (a few fast
+    particles dominate), mean density to 0.15 %, centre of mass to 0.006 / 0.027 (steps 25 / 100).
+    So KE is gated at step 25 and only density / centre of mass / sanity at step 100."""
     pos, vel, rho0, _ = _scene("two_blocks")
-    steps = 100
-    g = _gpu(rho0); g.upload(pos, vel); g.step(steps)
-    Pg, Vg, Rg = g.download()
-    o = _oracle(rho0, 64); o.upload(pos, vel); o.step(steps)
-    Po, Vo, Ro = o.download()
     diag = np.linalg.norm([2.0, 1.49, 2.0])
+    g = _gpu(rho0); g.upload(pos, vel)
+    o = _oracle(rho0, 64); o.upload(pos, vel)
+    g.step(25); o.step(25)
+    Pg, Vg, Rg = g.download(); Po, Vo, Ro = o.download()
+    keg, keo = 0.5 * (Vg ** 2).sum(), 0.5 * (Vo ** 2).sum()
+    assert abs(keg - keo) <= 0.05 * keo, (keg, keo)
     assert abs(Rg.mean() - Ro.mean()) / rho0 <= 0.01
     assert np.linalg.norm(Pg.mean(axis=0) - Po.mean(axis=0)) <= 0.01 * diag
-    keg, keo = 0.5 * (Vg ** 2).sum(), 0.5 * (Vo ** 2).sum()
-    assert abs(keg - keo) <= 0.05 * max(keo, 1e-9) + 0.5      # tiny absolute KE once the fluid is at rest
-    assert np.isfinite(Pg).all() and Pg[:, 1].min() >= 0.0
+    g.step(75); o.step(75)
+    Pg, Vg, Rg = g.download(); Po, Vo, Ro = o.download()
+    assert abs(Rg.mean() - Ro.mean()) / rho0 <= 0.01
+    assert np.linalg.norm(Pg.mean(axis=0) - Po.mean(axis=0)) <= 0.03 * diag
+    assert np.isfinite(Pg).all() and np.isfinite(Vg).all()
+    assert (Pg >= [-1, 0, -1]).all() and (Pg <= [1, 1.49, 1]).all()
     dg, cg = g.neighbor_digest(); do, co = o.digest()
     hg = np.bincount(cg, minlength=200)[:200] / len(cg); ho = np.bincount(co, minlength=200)[:200] / len(co)
     assert np.abs(hg - ho).sum() <= 0.30   # L1 distance of neighbour-count histograms (2106 particles: noisy)
+    assert abs(cg.mean() - co.mean()) <= 0.05 * co.mean()
 
 
 def test_large_block_properties():
@@ -241,10 +250,12 @@ def test_large_block_properties():
         assert dg.sum(dtype=np.uint64) == (mix * cg.astype(np.uint64)).sum(dtype=np.uint64)
     assert int(cg.sum()) % 2 == 0
     interior = cg.reshape(nx, ny, nz)[5:-5, 5:-5, 5:-5]
-    assert interior.min() >= 100 and interior.max() <= 140     # |r| <= 3 spacings: 122 lattice sites (jittered)
+    # |r| <= 3 spacings: 122 lattice sites, 30 of them at distance exactly H (knife edge): with
+    # jitter each of those is in or out at random, so the count is 92..122, mean 107.
+    assert interior.min() >= 92 and interior.max() <= 122 and abs(interior.mean() - 107.0) < 1.0
     P, V, R = g.download()
     assert np.isfinite(P).all() and np.isfinite(V).all() and np.isfinite(R).all()
-    assert (P >= np.array(box_min)).all() and (P <= np.array(box_max)).all()
+    assert (P >= np.array(box_min)).all() and (P <= np.float32(box_max).astype(np.float64)).all()   # device box is fp32
     # oracle (fp32) on the same input restricted to a corner sub-block would see different
     # neighbours at the cut, so compare the whole block against the oracle at reduced size instead
     ps, vs = lattice_block(24, 24, 24, jitter=0.001, seed=1234)
@@ -254,4 +265,12 @@ def test_large_block_properties():
     o.upload(ps, vs); o.step(1)
     assert np.array_equal(gs.neighbor_digest()[0], o.digest()[0])
     Pg, _, Rg = gs.download(); Po, _, Ro = o.download()
-    _gate_whole_step("24^3 block", Pg, Rg, Po, Ro, 700.0)
+    # This first step is violent (initial density 1062 -> 700) and coordinates reach 2.4, so the
+    # fp32 noise floor is above the Cornell-box one.  Self-calibrating gate: the GPU may differ from
+    # the fp32 oracle by no more than the fp32 oracle differs from the fp64 oracle (measured here:
+    # p50 2.5e-5, p99 6.1e-4, max 1.1e-2), i.e. it is inside the fp32 noise of the algorithm itself.
+    o64 = Oracle(oracle_params(rest_density=700.0, box_min=box_min, box_max=box_max, y_light=15.0, z_front=10.1), 64, COLLIDE_BOX, SEARCH_GRID)
+    o64.upload(ps, vs); o64.step(1)
+    P64, _, _ = o64.download()
+    floor = np.percentile(np.linalg.norm(Po - P64, axis=1), 50)
+    _gate_whole_step("24^3 block", Pg, Rg, Po, Ro, 700.0, p50_gate=max(1e-5, floor))
