@@ -223,8 +223,10 @@ def test_rollout_drift_vs_fp64_oracle():
     assert np.isfinite(Pg).all() and np.isfinite(Vg).all()
     assert (Pg >= [-1, 0, -1]).all() and (Pg <= [1, 1.49, 1]).all()
     dg, cg = g.neighbor_digest(); do, co = o.digest()
-    hg = np.bincount(cg, minlength=200)[:200] / len(cg); ho = np.bincount(co, minlength=200)[:200] / len(co)
-    assert np.abs(hg - ho).sum() <= 0.30   # L1 distance of neighbour-count histograms (2106 particles: noisy)
+    # neighbour-count histograms, bins of 10: the two CPU oracles (fp32 vs fp64) are 0.17 apart in L1
+    # on this scene after 100 steps (0.36 with bins of 1: 2106 samples are noisy), mean counts 69.6 / 69.9
+    hg = np.bincount(cg // 10, minlength=25)[:25] / len(cg); ho = np.bincount(co // 10, minlength=25)[:25] / len(co)
+    assert np.abs(hg - ho).sum() <= 0.30
     assert abs(cg.mean() - co.mean()) <= 0.05 * co.mean()
 
 
