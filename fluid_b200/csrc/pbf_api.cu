@@ -28,7 +28,8 @@ template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(
 
 // Parameters in fp32, computed with plain IEEE float operations (this TU is host code compiled by
 // the host compiler without fast-math; no contraction is possible on constants folded here).
-int fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
+}  // namespace
+int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   if (!(p.h > 0) || !(p.dt > 0) || !(p.rest_density > 0) || p.iterations < 0 || p.n_corr < 0) { err = "invalid PbfParams"; return PBF_ERR_INVALID; }
   if (p.xsph_mode != PBF_XSPH_JACOBI) { err = "the GPU path implements PBF_XSPH_JACOBI only (SURVEY.md 7.3-3)"; return PBF_ERR_INVALID; }
   volatile float h = (float)p.h;
@@ -60,8 +61,10 @@ int fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   }
   d.yl = (float)p.y_light; d.zf = (float)p.z_front;
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
+  d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
   return PBF_OK;
 }
+namespace {
 
 void free_arrays(pbf_handle* h) {
   for (int b = 0; b < 2; b++) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->orig[b]); h->pos[b] = h->vel[b] = nullptr; h->orig[b] = nullptr; }
@@ -73,10 +76,13 @@ void free_arrays(pbf_handle* h) {
   h->cap = 0; h->nbr_cap_rows = 0;
 }
 
-int ensure_capacity(pbf_handle* h, size_t n) {
-  if (n <= h->cap) return PBF_OK;
+}  // namespace
+// capacity in particles (sorted entries incl. ghosts and append slots); +1 for the sentinel
+int pbf::alloc_particle_arrays(Solver* hs, size_t n) {
+  pbf_handle* h = static_cast<pbf_handle*>(hs);
+  if (n + 1 <= h->cap) return PBF_OK;
   free_arrays(h);
-  const size_t cap = (n + 1 + 31) / 32 * 32;   // +1: the sentinel particle lives at index n
+  const size_t cap = (n + 1 + 31) / 32 * 32;   // +1: the sentinel particle lives at index n_sorted
   for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
   CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
   CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap));
@@ -94,6 +100,8 @@ int ensure_capacity(pbf_handle* h, size_t n) {
   h->cap = cap;
   return PBF_OK;
 }
+namespace {
+int ensure_capacity(pbf_handle* h, size_t n) { return alloc_particle_arrays(h, n); }
 
 // double <-> float conversion of big host arrays, spread over a few host threads
 template <class F> void parallel_for(size_t n, F fn) {
@@ -135,6 +143,16 @@ int check_device_errors(pbf_handle* h) {
 }
 
 }  // namespace
+
+int pbf::sync_and_check(Solver* hs) {
+  pbf_handle* h = static_cast<pbf_handle*>(hs);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaGetLastError());
+  if (h->call_timed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]); h->last_call_ms = ms; h->call_timed = false; }
+  h->prof_collect();
+  return check_device_errors(h);
+}
 
 // pinned staging lives outside the struct so pbf_internal.h stays CUDA-only
 struct HandleExtra { PinnedBuf pin; };
@@ -206,7 +224,8 @@ void pbf_destroy(pbf_handle* h) {
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->block_sums); cudaFree(h->sc);
   if (h->ev_call[0]) cudaEventDestroy(h->ev_call[0]);
   if (h->ev_call[1]) cudaEventDestroy(h->ev_call[1]);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+  for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   {
     std::lock_guard<std::mutex> g(g_extra_mu);
     auto it = g_extra.find(h);
@@ -225,7 +244,9 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   CK(h, cudaSetDevice(h->device));
   int rc = ensure_capacity(h, n);
   if (rc != PBF_OK) return rc;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
   h->n = n; h->cur = 0; h->have_neighbors = false;
+  h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   if (n == 0) return PBF_OK;
   HandleExtra* x = extra_of(h);
   CK(h, x->pin.ensure(6 * n));
@@ -245,7 +266,9 @@ int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const flo
   CK(h, cudaSetDevice(h->device));
   int rc = ensure_capacity(h, n);
   if (rc != PBF_OK) return rc;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
   h->n = n; h->cur = 0; h->have_neighbors = false;
+  h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   enqueue_import(h, d_pos_xyz, d_vel_xyz);
   CK(h, cudaStreamSynchronize(h->stream));
   CK(h, cudaGetLastError());
@@ -254,6 +277,7 @@ int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const flo
 
 int pbf_step(pbf_handle* h, int n_steps) {
   if (!h || n_steps < 0) return fail(h, PBF_ERR_INVALID, "pbf_step: bad argument");
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: drive the step through the pbf_slab_phase_* calls");
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaEventRecord(h->ev_call[0], h->stream));
   for (int s = 0; s < n_steps; s++) enqueue_step(h);
@@ -266,16 +290,12 @@ int pbf_step(pbf_handle* h, int n_steps) {
 
 int pbf_sync(pbf_handle* h) {
   if (!h) return PBF_ERR_INVALID;
-  CK(h, cudaSetDevice(h->device));
-  CK(h, cudaStreamSynchronize(h->stream));
-  CK(h, cudaGetLastError());
-  if (h->call_timed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]); h->last_call_ms = ms; h->call_timed = false; }
-  h->prof_collect();
-  return check_device_errors(h);
+  return sync_and_check(h);
 }
 
 int pbf_estimate_densities(pbf_handle* h) {
   if (!h) return PBF_ERR_INVALID;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "not available in slab mode");
   CK(h, cudaSetDevice(h->device));
   enqueue_estimate_densities(h);
   if (h->n > 0) h->have_neighbors = true;
@@ -336,7 +356,7 @@ int pbf_debug_capture(pbf_handle* h, int on) {
 int pbf_debug_neighbor_digest(pbf_handle* h, uint64_t* digest, uint32_t* count) {
   if (!h || !digest || !count) return PBF_ERR_INVALID;
   if (!h->have_neighbors) return fail(h, PBF_ERR_INVALID, "no neighbour lists yet: call pbf_step first");
-  const size_t n = h->n;
+  const size_t n = h->r_cnt;
   CK(h, cudaSetDevice(h->device));
   unsigned long long* dd = nullptr; uint32_t* dc = nullptr;
   CK(h, dmalloc(&dd, n)); CK(h, dmalloc(&dc, n));
@@ -355,6 +375,7 @@ int pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr, uint32_t* col
   if (!h->have_neighbors) return fail(h, PBF_ERR_INVALID, "no neighbour lists yet: call pbf_step first");
   int rc = pbf_sync(h);
   if (rc != PBF_OK) return rc;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "CSR download is single-GPU only (use the digest in slab mode)");
   const size_t n = h->n;
   Scalars s;
   CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));

@@ -26,7 +26,11 @@ struct DevParams {
   float yl, zf;               // virtual planes
   // uniform grid (cell edge slightly larger than h => 27-cell search is conservative)
   float inv_cell; float gmin[3];
-  int   gdim[3];              // cells per axis; linear id = (cx*gdim[1] + cy)*gdim[2] + cz  (z fastest)
+  int   gdim[3];              // LOCAL cells per axis; linear id = (cx*gdim[1] + cy)*gdim[2] + cz  (z fastest)
+  // slab decomposition along x: the grid is global (same gmin / inv_cell on every rank, so a
+  // position maps to the same cell everywhere); this rank stores columns cx_offset .. cx_offset+gdim[0]-1
+  // and owns the global columns [gx_lo, gx_hi).  Single GPU: cx_offset 0, owns everything.
+  int   gdim_x_global, cx_offset, gx_lo, gx_hi, hop_left, hop_right;
 };
 
 // ---- EXACT regime -------------------------------------------------------------------------------
@@ -116,14 +120,20 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
 // Cell coordinates of a position (clamped into the grid).  Conservative for the 27-cell search
 // because the cell edge is h*(1+2^-8) and fp32 rounding of (x-gmin)*inv_cell is << 2^-9 cells
 // for the domains we support (<= 2^12 cells per axis).
-__device__ __forceinline__ int3 cell_coords(const DevParams& P, float x, float y, float z) {
+__device__ __forceinline__ int3 cell_coords_global(const DevParams& P, float x, float y, float z) {
   int cx = (int)floorf((x - P.gmin[0]) * P.inv_cell);
   int cy = (int)floorf((y - P.gmin[1]) * P.inv_cell);
   int cz = (int)floorf((z - P.gmin[2]) * P.inv_cell);
-  cx = min(max(cx, 0), P.gdim[0] - 1);
+  cx = min(max(cx, 0), P.gdim_x_global - 1);
   cy = min(max(cy, 0), P.gdim[1] - 1);
   cz = min(max(cz, 0), P.gdim[2] - 1);
   return make_int3(cx, cy, cz);
+}
+// local cell coordinates (x column relative to this rank's first stored column)
+__device__ __forceinline__ int3 cell_coords(const DevParams& P, float x, float y, float z) {
+  int3 c = cell_coords_global(P, x, y, z);
+  c.x = min(max(c.x - P.cx_offset, 0), P.gdim[0] - 1);
+  return c;
 }
 __device__ __forceinline__ uint32_t cell_linear(const DevParams& P, int3 c) {
   return (uint32_t)((c.x * P.gdim[1] + c.y) * P.gdim[2] + c.z);

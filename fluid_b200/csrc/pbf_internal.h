@@ -18,7 +18,8 @@ struct Scalars {
   unsigned long long nbr_cursor;   // rows (of 32 entries) handed out by the neighbour build
   int err; int pad;
   double rho_first, rho_final;     // sum of densities: first lambda pass / finalize pass
-  unsigned int counters[8];        // slab packing cursors
+  unsigned int counters[8];        // slab packing cursors: emigrants L/R, ghosts L/R
+  unsigned int bounds[8];          // slab: cell_start at the column boundaries after the sort
 };
 
 enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
@@ -45,6 +46,18 @@ struct Solver {
   uint32_t *cell_count = nullptr, *cell_start = nullptr, *block_sums = nullptr;
   uint32_t *nbr = nullptr, *slice_off = nullptr, *nbr_cnt = nullptr;
   size_t nbr_cap_rows = 0;           // capacity of nbr in rows of 32 entries
+  // ranges of the cell-sorted arrays: [0, n_sorted) holds particles (ghost columns at both ends in
+  // slab mode); neighbour lists / solver passes cover the owned range [r_i0, r_i0 + r_cnt)
+  uint32_t n_sorted = 0, r_i0 = 0, r_cnt = 0;
+  // x-slab decomposition (pbf_slab.inl)
+  bool slab = false;
+  bool own_stream = true;
+  int has_left = 0, has_right = 0;
+  size_t halo_cap = 0;               // particles per migration / ghost message
+  float4 *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};     // [0] left, [1] right; element 0 = header
+  float4 *ghost_send[2] = {nullptr, nullptr}, *ghost_recv[2] = {nullptr, nullptr};
+  uint32_t bounds[5] = {0, 0, 0, 0, 0};   // b0..b3, n_sorted of the last slab sort (see pbf_b200_slab.h)
+  size_t n_in_cap() const { return slab ? cap : 0; }
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
   int capture_xpred = 0;
@@ -83,7 +96,17 @@ struct Solver {
 
 void enqueue_step(Solver* h);
 void enqueue_estimate_densities(Solver* h);
-void sort_and_build(Solver* h, int apply_forces, int include_self);
+void enqueue_predict_hash(Solver* h, int apply_forces);
+void enqueue_sort(Solver* h, size_t n_in);
+void enqueue_build(Solver* h, int include_self);
+void enqueue_lambda(Solver* h, int first_iter);
+void enqueue_delta(Solver* h);
+void enqueue_velocity(Solver* h);
+void enqueue_vorticity(Solver* h);
+void enqueue_confine(Solver* h);
+int  alloc_particle_arrays(Solver* h, size_t cap);          // pbf_api.cu
+int  fill_dev_params(const PbfParams& p, DevParams& d, std::string& err);
+int  sync_and_check(Solver* h);
 void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz);
 void enqueue_export3(Solver* h, const float4* src, float* dst_xyz);
 void enqueue_export1(Solver* h, const float* src, float* dst);

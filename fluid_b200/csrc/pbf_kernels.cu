@@ -13,6 +13,7 @@ namespace pbf {
 static constexpr int TPB = 256;          // threads per block for per-particle kernels
 static constexpr int SCAN_ITEMS = 8;     // items per thread in the cell scan
 static constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+static constexpr uint32_t CELL_INVALID = 0xFFFFFFFFu;
 
 __device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x, v.y, v.z); }
 
@@ -20,17 +21,23 @@ __device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x,
 // A. predict + collide + hash      (applyForceVelocity + clamp_response, particles.cpp:175-183,87-132)
 // EXACT regime: x* is bit-identical to the fp32 oracle.
 // ------------------------------------------------------------------------------------------------
+// Slab mode: a particle whose predicted position leaves the owned cell columns [gx_lo, gx_hi) is an
+// emigrant: it is packed (3 float4: x with the global id in .w, x*, v) into the message for the
+// x-neighbour and dropped from the local sort (cell_of stays INVALID).  Single-GPU mode owns every
+// column, so nothing ever emigrates.
 __global__ void __launch_bounds__(TPB)
-k_predict_hash(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ pos,
-               float4* __restrict__ vel, float4* __restrict__ xs_tmp, uint32_t* __restrict__ cell_of,
-               uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count, int apply_forces,
+k_predict_hash(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ pos,
+               float4* __restrict__ vel, const uint32_t* __restrict__ orig, float4* __restrict__ xs_tmp,
+               uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count,
+               int apply_forces, float4* __restrict__ mig_left, float4* __restrict__ mig_right, uint32_t mig_cap,
                Scalars* __restrict__ sc) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t i = i0 + t;
   const float4 x = pos[i];
   float3 p = xyz(x);
+  float4 v = vel[i];
   if (apply_forces) {
-    float4 v = vel[i];
     v.y = __fsub_rn(v.y, P.gdt);                                   // velocity.y -= 10 * delta_t
     const float3 delta = make_float3(__fmul_rn(v.x, P.dt), __fmul_rn(v.y, P.dt), __fmul_rn(v.z, P.dt));
     p = ex_collide(P, p, delta, true);
@@ -38,7 +45,20 @@ k_predict_hash(const __grid_constant__ DevParams P, uint32_t n, const float4* __
   }
   if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { atomicOr(&sc->err, ERRBIT_NONFINITE); p = make_float3(P.clo[0], P.clo[1], P.clo[2]); }
   xs_tmp[i] = make_float4(p.x, p.y, p.z, 0.f);
-  const uint32_t c = cell_linear(P, cell_coords(P, p.x, p.y, p.z));
+  const int3 cg = cell_coords_global(P, p.x, p.y, p.z);
+  if (cg.x < P.gx_lo || cg.x >= P.gx_hi) {
+    const int side = cg.x < P.gx_lo ? 0 : 1;
+    float4* dst = side ? mig_right : mig_left;
+    // one hop only: the neighbour slab must own the landing column
+    if (dst == nullptr || cg.x < P.gx_lo - P.hop_left || cg.x >= P.gx_hi + P.hop_right) { atomicOr(&sc->err, ERRBIT_MIGRATION); return; }
+    const uint32_t slot = atomicAdd(&sc->counters[side], 1u);
+    if (slot >= mig_cap) { atomicOr(&sc->err, ERRBIT_HALO_CAPACITY); return; }
+    dst[1 + 3 * slot + 0] = make_float4(x.x, x.y, x.z, __uint_as_float(orig[i]));
+    dst[1 + 3 * slot + 1] = make_float4(p.x, p.y, p.z, 0.f);
+    dst[1 + 3 * slot + 2] = v;
+    return;                                                        // cell_of[i] stays INVALID
+  }
+  const uint32_t c = cell_linear(P, make_int3(cg.x - P.cx_offset, cg.y, cg.z));
   cell_of[i] = c;
   rank[i] = atomicAdd(&cell_count[c], 1u);
 }
@@ -114,7 +134,9 @@ k_scatter(uint32_t n, const uint32_t* __restrict__ cell_of, const uint32_t* __re
           uint32_t* __restrict__ perm, uint32_t* __restrict__ key) {
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  const uint32_t slot = cell_start[cell_of[i]] + rank[i];
+  const uint32_t c = cell_of[i];
+  if (c == CELL_INVALID) return;            // emigrant, stale ghost or unused append slot
+  const uint32_t slot = cell_start[c] + rank[i];
   perm[slot] = i;
   key[slot] = orig[i];
 }
@@ -138,12 +160,12 @@ k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* _
 }
 
 __global__ void __launch_bounds__(TPB)
-k_reorder(uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
+k_reorder(uint32_t n_upper, const uint32_t* __restrict__ n_sorted_ptr, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
           const float4* __restrict__ pos_in, const float4* __restrict__ vel_in, const float4* __restrict__ xs_tmp,
           float4* __restrict__ pos_out, float4* __restrict__ vel_out, float4* __restrict__ xs_out,
           uint32_t* __restrict__ orig_out) {
   const uint32_t s = blockIdx.x * TPB + threadIdx.x;
-  if (s >= n) return;
+  if (s >= n_upper || s >= *n_sorted_ptr) return;     // n_sorted = cell_start[ncell], known on the device
   const uint32_t i = perm[s];
   pos_out[s] = pos_in[i];
   vel_out[s] = vel_in[i];
@@ -161,13 +183,15 @@ k_reorder(uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restr
 // truncation, ever.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB)
-k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt_range, uint32_t sentinel,
+                  const float4* __restrict__ xs,
                   const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ nbr,
                   uint32_t* __restrict__ slice_off, uint32_t* __restrict__ nbr_cnt,
                   unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;     // index inside the owned range
+  const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
-  const bool valid = i < n;
+  const bool valid = t < cnt_range;
   float3 pi = make_float3(0.f, 0.f, 0.f);
   uint32_t jb[9], je[9];
 #pragma unroll
@@ -201,9 +225,9 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4*
   }
   off = __shfl_sync(0xffffffffu, off, 0);
   if (!valid) return;
-  if (off == ~0ull) { nbr_cnt[i] = 0; if (lane == 0) slice_off[i >> 5] = 0; return; }
-  if (lane == 0) slice_off[i >> 5] = (uint32_t)off;
-  nbr_cnt[i] = cnt;
+  if (off == ~0ull) { nbr_cnt[t] = 0; if (lane == 0) slice_off[t >> 5] = 0; return; }
+  if (lane == 0) slice_off[t >> 5] = (uint32_t)off;
+  nbr_cnt[t] = cnt;
   uint32_t* out = nbr + off * 128ull + lane * 4;
   uint32_t s = 0;
 #pragma unroll
@@ -212,7 +236,7 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t n, const float4*
       const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
       if (take) { out[(size_t)(s >> 2) * 128u + (s & 3u)] = j; s++; }
     }
-  for (; s & 3u; s++) out[(size_t)(s >> 2) * 128u + (s & 3u)] = n;       // sentinel padding
+  for (; s & 3u; s++) out[(size_t)(s >> 2) * 128u + (s & 3u)] = sentinel;   // sentinel padding
 }
 
 // the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
@@ -228,10 +252,10 @@ __global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* vtmp, f
 // Visit the frozen neighbours of the calling thread's particle: body(p_j float4, extra...) is
 // applied to 4 gathered neighbours per coalesced uint4 index load, with the next index row
 // prefetched while the current one is processed.
-#define PBF_FOR_NEIGHBORS(i, BODY)                                                                   \
+#define PBF_FOR_NEIGHBORS(t, BODY)                                                                   \
   {                                                                                                  \
-    const uint4* lst_ = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[(i) >> 5] * 32u + (threadIdx.x & 31); \
-    const uint32_t rows_ = (nbr_cnt[i] + 3u) >> 2;                                                   \
+    const uint4* lst_ = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[(t) >> 5] * 32u + (threadIdx.x & 31); \
+    const uint32_t rows_ = (nbr_cnt[t] + 3u) >> 2;                                                   \
     uint4 nx_ = rows_ ? __ldg(lst_) : make_uint4(0, 0, 0, 0);                                        \
     for (uint32_t r_ = 0; r_ < rows_; r_++) {                                                        \
       const uint4 jj_ = nx_;                                                                         \
@@ -253,12 +277,13 @@ __device__ __forceinline__ float block_sum_to_double(float v, double* target) {
 }
 
 __global__ void __launch_bounds__(TPB)
-k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs_in,
+k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs_in,
          float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
          const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
   float rho = 0.f;
-  if (i < n) {
+  if (t < n) {
     const float4 pi = xs_in[i];
     float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
 #define BODY_L(J)                                                          \
@@ -271,7 +296,7 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restri
       gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz);    \
       dsum = fmaf(g * g, r2, dsum);                                        \
     }
-    PBF_FOR_NEIGHBORS(i, BODY_L)
+    PBF_FOR_NEIGHBORS(t, BODY_L)
 #undef BODY_L
     rho = P.poly6_c * w3s;
     const float gs = P.spiky_c * P.inv_rho0;            // grad_j C_i = gs * g * r_vec
@@ -292,11 +317,12 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t n, const float4* __restri
 // ------------------------------------------------------------------------------------------------
 template <int NCORR>
 __global__ void __launch_bounds__(TPB)
-k_delta(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs_in,
+k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
         const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
+  if (t >= n) return;
   const float4 pi = xs_in[i];
   float ax = 0.f, ay = 0.f, az = 0.f;
 #define BODY_D(J)                                                          \
@@ -312,7 +338,7 @@ k_delta(const __grid_constant__ DevParams P, uint32_t n, const float4* __restric
     const float f = (pi.w + pj.w - P.kcorr * qn) * g;                      \
     ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);      \
   }
-  PBF_FOR_NEIGHBORS(i, BODY_D)
+  PBF_FOR_NEIGHBORS(t, BODY_D)
 #undef BODY_D
   const float sc = P.spiky_c * P.inv_rho0;
   const float3 dp = make_float3(sc * ax, sc * ay, sc * az);
@@ -334,14 +360,15 @@ k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __rest
 }
 
 __global__ void __launch_bounds__(TPB)
-k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
                  const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
                  double* __restrict__ rho_sum) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
   float rho = 0.f;
-  if (i < n) {
+  if (t < n) {
     const float4 pi = xs[i];
     const float4 vi = vtmp[i];
     float w3s = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
@@ -359,7 +386,7 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t n, const float4* 
       sx = fmaf(w3, ux, sx); sy = fmaf(w3, uy, sy); sz = fmaf(w3, uz, sz);            \
       w3s += w3;                                                                      \
     }
-    PBF_FOR_NEIGHBORS(i, BODY_V)
+    PBF_FOR_NEIGHBORS(t, BODY_V)
 #undef BODY_V
     rho = P.poly6_c * w3s;
     ox *= P.spiky_c; oy *= P.spiky_c; oz *= P.spiky_c;
@@ -372,12 +399,13 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t n, const float4* 
 }
 
 __global__ void __launch_bounds__(TPB)
-k_confine_commit(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
                  const float4* __restrict__ omega, float4* __restrict__ vel, float4* __restrict__ pos,
                  const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
                  const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
+  if (t >= n) return;
   const float4 pi = xs[i];
   if (P.enable_vorticity) {
     float ex = 0.f, ey = 0.f, ez = 0.f;
@@ -391,7 +419,7 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t n, const float4* 
       const float f = wn * g;      /* |omega_j| * grad W (no own term, Q13) */ \
       ex = fmaf(f, dx, ex); ey = fmaf(f, dy, ey); ez = fmaf(f, dz, ez);    \
     }
-    PBF_FOR_NEIGHBORS(i, BODY_C)
+    PBF_FOR_NEIGHBORS(t, BODY_C)
 #undef BODY_C
     ex *= P.spiky_c; ey *= P.spiky_c; ez *= P.spiky_c;
     const float en = sqrtf(ex * ex + ey * ey + ez * ez);
@@ -411,11 +439,12 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t n, const float4* 
 
 // load-time density: sum of poly6 over the frozen set INCLUDING self (particles.cpp:158-163,440-444)
 __global__ void __launch_bounds__(TPB)
-k_density_only(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
+k_density_only(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
                float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
+  if (t >= n) return;
   const float4 pi = xs[i];
   float w3s = 0.f;
 #define BODY_R(J)                                                          \
@@ -426,7 +455,7 @@ k_density_only(const __grid_constant__ DevParams P, uint32_t n, const float4* __
     pair_terms(P, dx, dy, dz, r2, w3, g);                                  \
     w3s += w3;                                                             \
   }
-  PBF_FOR_NEIGHBORS(i, BODY_R)
+  PBF_FOR_NEIGHBORS(t, BODY_R)
 #undef BODY_R
   rho_out[i] = P.poly6_c * w3s;
 }
@@ -449,7 +478,7 @@ k_export3(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict
   const uint32_t s = blockIdx.x * TPB + threadIdx.x;
   if (s >= n) return;
   const float4 v = src[s];
-  const size_t o = orig[s];
+  const size_t o = orig ? orig[s] : s;
   dst_xyz[3 * o] = v.x; dst_xyz[3 * o + 1] = v.y; dst_xyz[3 * o + 2] = v.z;
 }
 
@@ -457,28 +486,30 @@ __global__ void __launch_bounds__(TPB)
 k_export1(uint32_t n, const float* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst) {
   const uint32_t s = blockIdx.x * TPB + threadIdx.x;
   if (s >= n) return;
-  dst[orig[s]] = src[s];
+  dst[orig ? orig[s] : s] = src[s];
 }
 
 __global__ void __launch_bounds__(TPB)
 k_export_w(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst) {
   const uint32_t s = blockIdx.x * TPB + threadIdx.x;
   if (s >= n) return;
-  dst[orig[s]] = src[s].w;
+  dst[orig ? orig[s] : s] = src[s].w;
 }
 
 __global__ void __launch_bounds__(TPB)
-k_neighbor_digest(uint32_t n, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
+k_neighbor_digest(uint32_t i0, uint32_t n, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
                   const uint32_t* __restrict__ nbr_cnt, const uint32_t* __restrict__ orig,
-                  unsigned long long* __restrict__ digest, uint32_t* __restrict__ count) {
-  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t cnt = nbr_cnt[i];
-  const uint32_t* lst = nbr + (size_t)slice_off[i >> 5] * 128u + (threadIdx.x & 31) * 4u;
+                  unsigned long long* __restrict__ digest, uint32_t* __restrict__ count, int by_orig) {
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t i = i0 + t;
+  if (t >= n) return;
+  const uint32_t cnt = nbr_cnt[t];
+  const uint32_t* lst = nbr + (size_t)slice_off[t >> 5] * 128u + (threadIdx.x & 31) * 4u;
   unsigned long long d = 0;
   for (uint32_t s = 0; s < cnt; s++) d += mix64((uint64_t)orig[lst[(size_t)(s >> 2) * 128u + (s & 3u)]]);
-  digest[orig[i]] = d;
-  count[orig[i]] = cnt;
+  const uint32_t o = by_orig ? orig[i] : t;   // slab mode: ids are global, so write in range order
+  digest[o] = d;
+  count[o] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -488,66 +519,99 @@ static inline unsigned blocks_for(size_t n, int per_block = TPB) { return (unsig
 
 #define LAUNCH(h, kid, kern, grid, ...)                                   \
   do {                                                                    \
-    (h)->prof_begin(kid);                                                 \
-    kern<<<(grid), TPB, 0, (h)->stream>>>(__VA_ARGS__);                   \
-    (h)->prof_end(kid);                                                   \
-    (h)->launches++;                                                      \
+    if ((grid) > 0) {                                                     \
+      (h)->prof_begin(kid);                                               \
+      kern<<<(grid), TPB, 0, (h)->stream>>>(__VA_ARGS__);                 \
+      (h)->prof_end(kid);                                                 \
+      (h)->launches++;                                                    \
+    }                                                                     \
   } while (0)
 
-// Sort the particles of pos/vel buffers `cur` by the cell of their predicted position (or of their
-// committed position when apply_forces == 0), leaving cell-sorted pos/vel/orig in buffers cur^1
-// and x* in xs_a; then build the frozen neighbour lists on xs_a.
-void sort_and_build(Solver* h, int apply_forces, int include_self) {
-  const uint32_t n = (uint32_t)h->n;
+// Phase 1 of the sort: clear the histogram, predict the owned range [r_i0, r_i0 + r_cnt) of the
+// current buffers (or just re-bin committed positions when apply_forces == 0) and hash it.
+void enqueue_predict_hash(Solver* h, int apply_forces) {
+  const int cur = h->cur;
+  cudaMemsetAsync(h->cell_count, 0, sizeof(uint32_t) * h->ncell, h->stream);
+  cudaMemsetAsync(h->cell_of, 0xFF, sizeof(uint32_t) * h->n_in_cap(), h->stream);
+  cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
+  cudaMemsetAsync(h->sc->counters, 0, sizeof(h->sc->counters), h->stream);
+  LAUNCH(h, K_PREDICT, k_predict_hash, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur],
+         h->xs_tmp, h->cell_of, h->rank, h->cell_count, apply_forces,
+         h->slab && h->has_left ? h->mig_send[0] : (float4*)nullptr, h->slab && h->has_right ? h->mig_send[1] : (float4*)nullptr,
+         (uint32_t)h->halo_cap, h->sc);
+}
+
+// Phase 2: scan, scatter the n_in entries of the unsorted arrays that carry a valid cell, canonical
+// in-cell order, reorder into buffers cur^1 / xs_a.  Leaves n_sorted on the device (cell_start[ncell]).
+void enqueue_sort(Solver* h, size_t n_in) {
   const uint32_t ncell = h->ncell;
   const int cur = h->cur, nxt = cur ^ 1;
-  cudaMemsetAsync(h->cell_count, 0, sizeof(uint32_t) * ncell, h->stream);
-  cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
-  LAUNCH(h, K_PREDICT, k_predict_hash, blocks_for(n), h->dp, n, h->pos[cur], h->vel[cur], h->xs_tmp, h->cell_of,
-         h->rank, h->cell_count, apply_forces, h->sc);
   const unsigned sb = blocks_for(ncell, SCAN_TILE);
   LAUNCH(h, K_SCAN, k_scan_reduce, sb, ncell, h->cell_count, h->block_sums);
   LAUNCH(h, K_SCAN, k_scan_block_sums, 1, sb, h->block_sums);
   LAUNCH(h, K_SCAN, k_scan_apply, sb, ncell, h->cell_count, h->block_sums, h->cell_start);
-  LAUNCH(h, K_SCATTER, k_scatter, blocks_for(n), n, h->cell_of, h->rank, h->cell_start, h->orig[cur], h->perm, h->key);
+  LAUNCH(h, K_SCATTER, k_scatter, blocks_for(n_in), (uint32_t)n_in, h->cell_of, h->rank, h->cell_start, h->orig[cur], h->perm, h->key);
   LAUNCH(h, K_CELLSORT, k_cell_sort, blocks_for(ncell), ncell, h->cell_start, h->perm, h->key);
-  LAUNCH(h, K_REORDER, k_reorder, blocks_for(n), n, h->perm, h->key, h->pos[cur], h->vel[cur], h->xs_tmp,
-         h->pos[nxt], h->vel[nxt], h->xs_a, h->orig[nxt]);
+  LAUNCH(h, K_REORDER, k_reorder, blocks_for(n_in), (uint32_t)n_in, h->cell_start + ncell, h->perm, h->key, h->pos[cur], h->vel[cur],
+         h->xs_tmp, h->pos[nxt], h->vel[nxt], h->xs_a, h->orig[nxt]);
   h->cur = nxt;
-  h->prof_begin(K_REORDER);
-  k_set_sentinel<<<1, 32, 0, h->stream>>>(n, h->xs_a, h->xs_b, h->vtmp, h->omega);
-  h->prof_end(K_REORDER); h->launches++;
-  LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(n), h->dp, n, h->xs_a, h->cell_start, h->nbr, h->slice_off,
-         h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
 }
 
+// Phase 3: frozen neighbour lists for the range [r_i0, r_i0 + r_cnt) of the n_sorted sorted particles.
+void enqueue_build(Solver* h, int include_self) {
+  h->prof_begin(K_REORDER);
+  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->vtmp, h->omega);
+  h->prof_end(K_REORDER); h->launches++;
+  LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
+         h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
+}
+
+void enqueue_lambda(Solver* h, int first_iter) {
+  LAUNCH(h, K_LAMBDA, k_lambda, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->xs_b, h->nbr, h->slice_off, h->nbr_cnt,
+         (float*)nullptr, first_iter ? &h->sc->rho_first : (double*)nullptr);
+}
+void enqueue_delta(Solver* h) {
+  const unsigned g = blocks_for(h->r_cnt);
+  if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, h->r_i0, h->r_cnt, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+  else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, h->r_i0, h->r_cnt, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+}
+void enqueue_velocity(Solver* h) {   // every sorted particle, ghosts included (their x and x* are bit-identical to the owner's)
+  LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp);
+}
+void enqueue_vorticity(Solver* h) {
+  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->vtmp, h->vel[h->cur], h->omega,
+         h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
+}
+void enqueue_confine(Solver* h) {
+  LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->omega, h->vel[h->cur],
+         h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt);
+}
+
+// single-GPU step: every particle is owned, n never changes, nothing needs a host round trip
 void enqueue_step(Solver* h) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;
-  const unsigned g = blocks_for(n);
   cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);   // rho_first, rho_final
-  sort_and_build(h, 1, 0);
-  const int cur = h->cur;
+  h->r_i0 = 0; h->r_cnt = n; h->n_sorted = n;
+  enqueue_predict_hash(h, 1);
+  enqueue_sort(h, n);
+  enqueue_build(h, 0);
   if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
-  for (int it = 0; it < h->dp.iterations; it++) {
-    LAUNCH(h, K_LAMBDA, k_lambda, g, h->dp, n, h->xs_a, h->xs_b, h->nbr, h->slice_off, h->nbr_cnt,
-           (float*)nullptr, it == 0 ? &h->sc->rho_first : (double*)nullptr);
-    if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
-    else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, n, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
-  }
-  LAUNCH(h, K_VELOCITY, k_velocity, g, h->dp, n, h->xs_a, h->pos[cur], h->vtmp);
-  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, g, h->dp, n, h->xs_a, h->vtmp, h->vel[cur], h->omega, h->rho, h->nbr,
-         h->slice_off, h->nbr_cnt, &h->sc->rho_final);
-  LAUNCH(h, K_CONFINE, k_confine_commit, g, h->dp, n, h->xs_a, h->omega, h->vel[cur], h->pos[cur], h->nbr,
-         h->slice_off, h->nbr_cnt);
+  for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0); enqueue_delta(h); }
+  enqueue_velocity(h);
+  enqueue_vorticity(h);
+  enqueue_confine(h);
   h->steps_done++;
 }
 
 void enqueue_estimate_densities(Solver* h) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;
-  sort_and_build(h, 0, 1);
-  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt);
+  h->r_i0 = 0; h->r_cnt = n; h->n_sorted = n;
+  enqueue_predict_hash(h, 0);
+  enqueue_sort(h, n);
+  enqueue_build(h, 1);
+  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, 0u, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt);
 }
 
 void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz) {
@@ -556,21 +620,20 @@ void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz) {
   LAUNCH(h, K_IO, k_import, blocks_for(n), n, d_pos_xyz, d_vel_xyz, h->pos[h->cur], h->vel[h->cur], h->orig[h->cur]);
 }
 
+// exports act on the owned range; dst index = original id (single GPU) or position in the range (slab)
 void enqueue_export3(Solver* h, const float4* src, float* dst_xyz) {
-  const uint32_t n = (uint32_t)h->n;
-  if (n) LAUNCH(h, K_IO, k_export3, blocks_for(n), n, src, h->orig[h->cur], dst_xyz);
+  if (h->r_cnt) LAUNCH(h, K_IO, k_export3, blocks_for(h->r_cnt), h->r_cnt, src + h->r_i0, h->slab ? (const uint32_t*)nullptr : h->orig[h->cur] + h->r_i0, dst_xyz);
 }
 void enqueue_export1(Solver* h, const float* src, float* dst) {
-  const uint32_t n = (uint32_t)h->n;
-  if (n) LAUNCH(h, K_IO, k_export1, blocks_for(n), n, src, h->orig[h->cur], dst);
+  if (h->r_cnt) LAUNCH(h, K_IO, k_export1, blocks_for(h->r_cnt), h->r_cnt, src + h->r_i0, h->slab ? (const uint32_t*)nullptr : h->orig[h->cur] + h->r_i0, dst);
 }
 void enqueue_export_w(Solver* h, const float4* src, float* dst) {
-  const uint32_t n = (uint32_t)h->n;
-  if (n) LAUNCH(h, K_IO, k_export_w, blocks_for(n), n, src, h->orig[h->cur], dst);
+  if (h->r_cnt) LAUNCH(h, K_IO, k_export_w, blocks_for(h->r_cnt), h->r_cnt, src + h->r_i0, h->slab ? (const uint32_t*)nullptr : h->orig[h->cur] + h->r_i0, dst);
 }
 void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count) {
-  const uint32_t n = (uint32_t)h->n;
-  if (n) LAUNCH(h, K_IO, k_neighbor_digest, blocks_for(n), n, h->nbr, h->slice_off, h->nbr_cnt, h->orig[h->cur], digest, count);
+  if (h->r_cnt) LAUNCH(h, K_IO, k_neighbor_digest, blocks_for(h->r_cnt), h->r_i0, h->r_cnt, h->nbr, h->slice_off, h->nbr_cnt, h->orig[h->cur], digest, count, h->slab ? 0 : 1);
 }
 
 }  // namespace pbf
+
+#include "pbf_slab.inl"

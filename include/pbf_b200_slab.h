@@ -1,0 +1,76 @@
+/* pbf_b200_slab.h — C ABI of the x-slab decomposition (one process per GPU).
+ *
+ * The reference is a single process; this part of the boundary has no reference counterpart.  It
+ * splits Particles::timeStep (particles.cpp:250-297) into phases so that a host-side driver
+ * (fluid_b200/slab.py, torch.distributed over NCCL) can exchange particles between x-adjacent
+ * ranks in between.  The library itself never communicates: it fills / consumes device message
+ * buffers whose addresses pbf_slab_buffer() hands out.
+ *
+ * Geometry.  The cell grid is GLOBAL (same origin and cell edge on every rank).  Rank r owns the
+ * cell columns [gx_lo, gx_hi) and stores one ghost column on each side.  After the per-step sort
+ * the arrays are ordered (column, cy, cz, global id), so with x slowest
+ *      [0,b0) left ghosts | [b0,b3) owned | [b3,n) right ghosts
+ * and the owner's boundary column [b0,b1) (resp. [b2,b3)) has the SAME order as the neighbour's
+ * ghost range: per-iteration halo refreshes are plain contiguous copies, no pack / unpack.
+ * Every floating-point sum runs in the same order as on one GPU, so an N-slab run reproduces the
+ * single-GPU run bit for bit.
+ *
+ * One step (driver's view):
+ *   pbf_slab_phase_predict   predict + collide owned particles; emigrants -> MIG_SEND_L/R
+ *   <exchange MIG_SEND_* -> neighbour's MIG_RECV_*>                       (fixed-size messages)
+ *   pbf_slab_phase_migrate   append immigrants; boundary columns -> GHOST_SEND_L/R
+ *   <exchange GHOST_SEND_* -> GHOST_RECV_*>
+ *   pbf_slab_phase_sort      append ghosts, counting sort, neighbour lists; returns b0..b3,n (syncs)
+ *   iterations x { pbf_slab_phase(LAMBDA) ; <copy XS_B[b0,b1) -> left's XS_B[b3',n'), XS_B[b2,b3) -> right's XS_B[0,b0')> ;
+ *                  pbf_slab_phase(DELTA)  ; <same for XS_A> }
+ *   pbf_slab_phase(VELOCITY) ; pbf_slab_phase(VORTICITY) ; <same copy for OMEGA> ; pbf_slab_phase(CONFINE)
+ */
+#ifndef PBF_B200_SLAB_H
+#define PBF_B200_SLAB_H
+
+#include "pbf_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Cells per axis of the global grid for these parameters (cell edge = h * (1 + 2^-8)). */
+int pbf_grid_dims(const PbfParams* params, int dims_out[3]);
+/* Global cell column of x positions (fp32 arithmetic identical to the device's). */
+int pbf_cell_columns(const PbfParams* params, size_t n, const double* pos_xyz, int32_t* column_out);
+
+/* Run all work of this handle on the caller's CUDA stream (e.g. torch's current stream). */
+int pbf_set_stream(pbf_handle* h, void* cuda_stream);
+
+/* This handle owns global cell columns [gx_lo, gx_hi); left_cols / right_cols = number of columns
+ * owned by the x-neighbours (0 = no neighbour on that side).  particle_cap bounds owned + ghost
+ * particles; halo_cap bounds each migration / ghost message (particles).  Call before uploading. */
+int pbf_slab_configure(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int right_cols,
+                       size_t particle_cap, size_t halo_cap);
+/* Owned particles of this rank with their GLOBAL ids (host, fp64 AoS). */
+int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz, const uint32_t* ids);
+/* Owned particles, in the rank's current sorted order (fp64 AoS) + ids; *n_out = count. */
+int pbf_slab_download(pbf_handle* h, size_t cap, double* pos_xyz, double* vel_xyz, double* density, uint32_t* ids, size_t* n_out);
+/* Neighbour digests of the owned particles, same order as pbf_slab_download. */
+int pbf_slab_neighbor_digest(pbf_handle* h, size_t cap, uint64_t* digest, uint32_t* count);
+
+int pbf_slab_phase_predict(pbf_handle* h);
+int pbf_slab_phase_migrate(pbf_handle* h);
+int pbf_slab_phase_sort(pbf_handle* h, uint32_t bounds_out[5]);   /* b0, b1, b2, b3, n ; synchronises */
+enum { PBF_PHASE_LAMBDA_FIRST = 0, PBF_PHASE_LAMBDA = 1, PBF_PHASE_DELTA = 2, PBF_PHASE_VELOCITY = 3,
+       PBF_PHASE_VORTICITY = 4, PBF_PHASE_CONFINE = 5 };
+int pbf_slab_phase(pbf_handle* h, int phase);
+/* sums over the owned particles of the last step: density after the first lambda pass / final, count */
+int pbf_slab_stats(pbf_handle* h, double* rho_first_sum, double* rho_final_sum, uint64_t* n_owned);
+
+/* Device buffers.  Message buffers are float4 arrays: element 0 is a header (count in .x as uint32
+ * bits), then 3 float4 per migrant (x|id, x*, v) or 2 per ghost (x*|id, x). */
+enum { PBF_BUF_MIG_SEND_L = 0, PBF_BUF_MIG_SEND_R = 1, PBF_BUF_MIG_RECV_L = 2, PBF_BUF_MIG_RECV_R = 3,
+       PBF_BUF_GHOST_SEND_L = 4, PBF_BUF_GHOST_SEND_R = 5, PBF_BUF_GHOST_RECV_L = 6, PBF_BUF_GHOST_RECV_R = 7,
+       PBF_BUF_XS_A = 8, PBF_BUF_XS_B = 9, PBF_BUF_OMEGA = 10 };
+void* pbf_slab_buffer(pbf_handle* h, int which, size_t* bytes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBF_B200_SLAB_H */
