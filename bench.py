@@ -31,6 +31,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL banners off stdout: rank 0 prints ONE JSON line
 
 import numpy as np
 

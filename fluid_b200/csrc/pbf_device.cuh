@@ -163,7 +163,7 @@ __device__ __forceinline__ void pair_terms(const DevParams& P, float dx, float d
   g = hr * hr * rinv;
 }
 
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t j) {   // == pbf_oracle::mix64
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t j) {   // splitmix64 finaliser (the digest function the header documents)
   uint64_t z = j + 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

@@ -1,0 +1,86 @@
+// particles_b200.h — host-side adapter with the reference's `Particles` interface
+// (SsnL/Fluid src/particles.h:105-140) on top of the C ABI (include/pbf_b200.h).
+//
+// The rest of the reference program touches the fluid only through this surface:
+//   Application::load_particles  (application.cpp:302-344): Particles(rho0), addParticle, estimateDensities
+//   PathTracer::fluid_simulate_* (pathtracer.cpp:444-480):  timeStep(), simulate_time
+//   Particles::redraw            (particles.cpp:303-307):   ps[i]->getPosition(), getDensityBasedColor()
+//   Particles::estimateDensityAt (particles.cpp:446-453):   marching cubes field
+// so a maintainer swaps `#include "particles.h"` for this header.  The solver
+// state lives on the GPU; `ps` is a host mirror refreshed by every timeStep().
+#pragma once
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include "../../include/pbf_b200.h"
+
+namespace pbfhost {
+
+struct Vector3D {   // CGL::Vector3D's data layout (three doubles); only what the adapter needs
+  double x, y, z;
+  Vector3D() : x(0), y(0), z(0) {}
+  Vector3D(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
+};
+
+struct Color { float r, g, b, a; };
+
+class Particle {   // particles.h:19-91: the read-only part the visualiser / surfacer use
+ public:
+  Vector3D velocity;
+  Particle(const Vector3D& p, const Vector3D& v, double rho0) : velocity(v), position(p), density(0), rest_density(rho0) {}
+  double getLatestDensityEstimate() const { return density; }
+  Vector3D getPosition() const { return position; }
+  Color getDensityBasedColor() const {   // particles.h:48-52
+    double ratio = (density - 0.8 * rest_density) / (0.4 * rest_density);
+    double c = ratio < 0.0 ? 0.0 : (ratio > 1.0 ? 1.0 : ratio);
+    return Color{1.0f, (float)(1.0 - c), (float)(1.0 - c), 1.0f};
+  }
+ private:
+  friend struct Particles;
+  Vector3D position;
+  double density;
+  double rest_density;
+};
+
+struct Particles {
+  std::vector<Particle*> ps;           // particles.h:106 (host mirror, original order)
+  double simulate_time;                // particles.h:109
+  const double rest_density;           // particles.h:110
+  bool surfaceUpToTimestep = false;    // particles.h:112
+  bool quiet = false;                  // the reference prints two lines per step (Q16); keep, but allow silence
+
+  explicit Particles(double rest_density = 1000.0, const PbfParams* params = nullptr, int device = 0);
+  ~Particles();
+  Particles(const Particles&) = delete;
+  Particles& operator=(const Particles&) = delete;
+
+  void addParticle(Vector3D pos, Vector3D v);    // particles.h:118-120
+  void timeStep(double delta_t);                 // particles.cpp:250-297 (delta_t must equal params.dt)
+  void timeStep();                               // particles.cpp:299-301
+  void estimateDensities();                      // particles.cpp:440-444
+  double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host; marching-cubes consumer)
+  std::string paramsString() const;              // particles.cpp:420-438
+  // the two numbers of the reference's "avg rho: a => b" line for the last step
+  double avg_rho_first_iter = 0.0, avg_rho_final = 0.0;
+  const PbfParams& params() const { return params_; }
+  const char* lastError() const;
+
+ private:
+  void ensureUploaded();
+  void refreshMirror();
+  PbfParams params_;
+  int device_;
+  pbf_handle* handle_ = nullptr;
+  bool uploaded_ = false;
+  std::vector<double> pos_, vel_, rho_;
+};
+
+// Application::load_particles (application.cpp:302-344): <particles><density>rho0</density><ps>
+// <particle><pos>x y z</pos><v>x y z</v></particle>...  Density goes through float like stof (Q17).
+// Streaming reader (no DOM), so multi-million-particle files are fine.  Returns nullptr on error.
+Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0);
+// parse only: positions / velocities (AoS doubles) and rho0; false on error
+bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::vector<double>& vel, double& rho0, std::string* error);
+
+}  // namespace pbfhost

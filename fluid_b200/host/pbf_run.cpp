@@ -1,0 +1,85 @@
+// pbf_run — windowless driver mirroring the reference's `pathtracer -p particles.xml -d seconds`
+// simulation loop (main.cpp:110-117,159-171; pathtracer.cpp:444-480) without the renderer:
+//   load_particles -> estimateDensities -> while (simulate_time < T) timeStep()   (63 steps / second, Q18)
+// Optional --dump writes the per-step state in the same PBFDUMP1 format as oracle/ref_harness.
+//   pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--iterations I]
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "particles_b200.h"
+
+using namespace pbfhost;
+
+int main(int argc, char** argv) {
+  const char* pfile = nullptr; const char* dump = nullptr;
+  double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "-p" && i + 1 < argc) pfile = argv[++i];
+    else if (a == "-d" && i + 1 < argc) seconds = atof(argv[++i]);
+    else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
+    else if (a == "--iterations" && i + 1 < argc) iterations = atoi(argv[++i]);
+    else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
+    else if (a == "--quiet") quiet = true;
+    else if (a == "--parse-only") parse_only = true;
+    else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only]\n"); return 2; }
+  }
+  if (!pfile) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
+  std::string err;
+  if (parse_only) {
+    std::vector<double> pos, vel; double rho0 = 0;
+    if (!parse_particles_xml(pfile, pos, vel, rho0, &err)) { printf("[ERROR] XML error: %s\n", err.c_str()); return 1; }
+    double sp = 0, sv = 0;
+    for (double v : pos) sp += v;
+    for (double v : vel) sv += v;
+    printf("{\"n\": %zu, \"rho0\": %.17g, \"sum_pos\": %.17g, \"sum_vel\": %.17g}\n", pos.size() / 3, rho0, sp, sv);
+    return 0;
+  }
+  PbfParams prm; pbf_default_params(&prm);
+  if (iterations >= 0) prm.iterations = iterations;
+  printf("[Fluid Simulation] Loading particle file...");
+  Particles* ps = load_particles_xml(pfile, &err, &prm, 0);
+  if (!ps) { printf("[ERROR] XML error: %s\n", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
+  printf("Done!\n");
+  ps->quiet = quiet;
+  const int64_t n = (int64_t)ps->ps.size();
+  if (steps < 0 && seconds < 0) steps = 1;
+  FILE* f = dump ? fopen(dump, "wb") : nullptr;
+  std::vector<std::vector<double>> frames;
+  auto t0 = std::chrono::steady_clock::now();
+  int done = 0;
+  const double start = ps->simulate_time;
+  while (steps >= 0 ? done < steps : ps->simulate_time < start + seconds) {   // pathtracer.cpp:454,475
+    ps->timeStep();
+    done++;
+    if (f) {
+      std::vector<double> st(8 * n);
+      for (int64_t i = 0; i < n; i++) {
+        const Particle* p = ps->ps[i];
+        Vector3D x = p->getPosition();
+        st[8*i] = x.x; st[8*i+1] = x.y; st[8*i+2] = x.z;
+        st[8*i+3] = p->velocity.x; st[8*i+4] = p->velocity.y; st[8*i+5] = p->velocity.z;
+        st[8*i+6] = p->getLatestDensityEstimate(); st[8*i+7] = 0.0;
+      }
+      frames.push_back(std::move(st));
+    }
+  }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (f) {
+    int64_t hdr[2] = {n, done};
+    fwrite("PBFDUMP1", 1, 8, f); fwrite(hdr, 8, 2, f);
+    std::vector<int32_t> zero(n, 0);
+    double per = done ? secs / done : 0.0;
+    for (auto& st : frames) { fwrite(st.data(), 8, st.size(), f); fwrite(zero.data(), 4, n, f); fwrite(&per, 8, 1, f); }
+    fclose(f);
+  }
+  fprintf(stderr, "{\"n\": %lld, \"steps\": %d, \"seconds_total\": %.6f, \"ms_per_step_incl_readback\": %.4f}\n", (long long)n, done, secs,
+          done ? 1e3 * secs / done : 0.0);
+  delete ps;
+  return 0;
+}

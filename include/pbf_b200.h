@@ -94,7 +94,8 @@ int  pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, floa
 
 /* ---- parity / debug ---------------------------------------------------------------------- */
 /* Order-independent 64-bit digest and size of each particle's frozen neighbour set of the last
- * step, in ORIGINAL indices (sum over neighbours j of mix64(j)); see oracle/pbf_oracle.hpp. */
+ * step, in ORIGINAL indices: sum over neighbours j of mix64(j), mix64 = splitmix64 finaliser of
+ * (j + 0x9E3779B97F4A7C15). */
 int  pbf_debug_neighbor_digest(pbf_handle* h, uint64_t* per_particle_digest, uint32_t* per_particle_count);
 /* CSR of the frozen neighbour sets, original indices, ascending within a row (small N). */
 int  pbf_debug_download_neighbors(pbf_handle* h, uint32_t* row_ptr /*n+1*/, uint32_t* col_idx, size_t col_cap);

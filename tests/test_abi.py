@@ -1,0 +1,86 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/*.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = set()
+    for hdr in ("pbf_b200.h", "pbf_b200_slab.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms |= set(re.findall(r"\b(pbf_[a-z0-9_]+)\s*\(", text))
+    return syms
+
+
+def test_library_exports_every_declared_symbol():
+    from fluid_b200 import api
+    lib = api.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in sorted(syms) if not hasattr(lib, s)]
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+
+
+def test_library_is_sm100a_cuda_and_independent_of_oracle_and_torch():
+    from fluid_b200 import build
+    so = build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "oracle" not in ldd
+    # no product source mentions the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fluid_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "pbf_oracle" not in text and "import helpers" not in text, f
+
+
+def test_default_params_are_the_reference_macros():
+    """particles.cpp:24-44 and the hard-coded box of clamp()/clamp_response() (59-83)."""
+    from fluid_b200 import api
+    p = api.default_params()
+    assert (p.h, p.dt, p.eps_relax, p.k_corr, p.dq_ratio, p.visc_c, p.vort_eps, p.gravity_y) == (0.3, 0.016, 2.0, 0.0001, 0.1, 0.001, 0.001, -10.0)
+    assert (p.n_corr, p.iterations, p.rest_density) == (4, 12, 1000.0)
+    assert list(p.box_min) == [-1.0, 0.0, -1.0] and list(p.box_max) == [1.0, 1.49, 1.0]
+    assert (p.y_light, p.z_front, p.xsph_mode, p.enable_vorticity, p.enable_xsph) == (1.49, 1.0, 0, 1, 1)
+    # the oracle's mirror of the struct has the same layout
+    import helpers
+    assert C.sizeof(api.PbfParams) == C.sizeof(helpers.PbfParams)
+    q = helpers.default_params()
+    assert bytes(p) == bytes(q)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fluid_b200 import api
+    lib = api.load_library()
+    assert lib.pbf_device_count() == 0
+    with pytest.raises(api.PbfError) as e:
+        api.Solver(api.default_params())
+    assert e.value.code == api.PBF_ERR_NO_DEVICE
+
+
+def test_grid_dims_and_columns_on_host():
+    """pbf_grid_dims / pbf_cell_columns are pure host functions (used by the slab planner)."""
+    from fluid_b200 import api, slab
+    lib = slab._bind(api.load_library())
+    p = api.default_params(box_min=(0, 0, 0), box_max=(120.0, 30.0, 20.1))
+    dims = (C.c_int * 3)()
+    assert lib.pbf_grid_dims(C.byref(p), C.byref(dims)) == 0
+    cell = np.float32(0.3) * (np.float32(1) + np.float32(1 / 256))
+    assert list(dims) == [int(np.floor(120.0 / float(cell))) + 1, int(np.floor(30.0 / float(cell))) + 1, int(np.floor(20.1 / float(cell))) + 1]
+    x = np.array([[0.0, 1, 1], [0.30, 1, 1], [0.302, 1, 1], [119.99, 1, 1], [500.0, 1, 1]])
+    col = np.empty(5, dtype=np.int32)
+    assert lib.pbf_cell_columns(C.byref(p), 5, x.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p)) == 0
+    assert list(col) == [0, 0, 1, int(np.floor(np.float32(119.99) / cell)), dims[0] - 1]

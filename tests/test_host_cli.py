@@ -1,0 +1,66 @@
+"""The C++ host adapter (fluid_b200/host): XML import like Application::load_particles
+(application.cpp:302-344) and the windowless -p/-d loop (pathtracer.cpp:444-480)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, read_dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "fluid_b200", "host")
+
+
+def _build():
+    from fluid_b200 import build
+    build.build()
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    return os.path.join(HOST, "pbf_run")
+
+
+def _write_xml(path, pos, vel, rho0):
+    with open(path, "w") as f:
+        f.write("<?xml version=\"1.0\"?>\n<!-- generated -->\n<particles>\n  <density>%r</density>\n  <ps>\n" % float(rho0))
+        for p, v in zip(pos, vel):
+            f.write("    <particle>\n      <pos>%r %r %r</pos>\n      <v>%r %r %r</v>\n    </particle>\n" % (*map(float, p), *map(float, v)))
+        f.write("  </ps>\n</particles>\n")
+
+
+def test_xml_loader_matches_reference_parse(tmp_path):
+    exe = _build()
+    sc = np.load(os.path.join(GOLDEN, "scene_spheres_p.npz"))
+    xml = str(tmp_path / "s.xml")
+    _write_xml(xml, sc["pos"], sc["vel"], float(sc["rho0"]))
+    out = json.loads(subprocess.run([exe, "-p", xml, "--parse-only"], check=True, capture_output=True, text=True).stdout)
+    assert out["n"] == 2106 and out["rho0"] == 700.0
+    assert out["sum_pos"] == float(np.sum(sc["pos"].reshape(-1).cumsum()[-1:])) or abs(out["sum_pos"] - sc["pos"].sum()) < 1e-9
+    assert out["sum_vel"] == -2106.0
+    # malformed files are reported, not crashed on
+    bad = str(tmp_path / "bad.xml"); open(bad, "w").write("<notparticles/>")
+    r = subprocess.run([exe, "-p", bad, "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "XML error" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
+    exe = _build()
+    ref = np.load(os.path.join(GOLDEN, "ref_jitter_two_blocks.npz"))
+    xml = str(tmp_path / "s.xml"); dump = str(tmp_path / "d.bin")
+    _write_xml(xml, ref["pos"], ref["vel"], float(ref["rho0"]))
+    r = subprocess.run([exe, "-p", xml, "--steps", "2", "--dump", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("avg rho:") == 2
+    d = read_dump(dump)
+    from fluid_b200 import api
+    g = api.Solver(api.default_params(rest_density=float(ref["rho0"])))
+    g.upload(ref["pos"], ref["vel"]); g.estimate_densities(); g.step(1)
+    P, V, R = g.download()
+    assert np.array_equal(d[0]["state"][:, 0:3], P) and np.array_equal(d[0]["state"][:, 3:6], V) and np.array_equal(d[0]["state"][:, 6], R)
+    # step 0 against the unmodified reference's output
+    dx = np.linalg.norm(d[0]["state"][:, 0:3] - ref["state_0"][:, 0:3], axis=1)
+    assert np.percentile(dx, 50) <= 1e-5 and np.percentile(dx, 99) <= 5e-3 and dx.max() <= 1e-1
+    # -d 0.05 => ceil(0.05/0.016) = 4 steps (while simulate_time < T, Q18)
+    r = subprocess.run([exe, "-p", xml, "-d", "0.05", "--quiet"], capture_output=True, text=True)
+    assert json.loads(r.stderr.strip().splitlines()[-1])["steps"] == 4
