@@ -82,7 +82,9 @@ int pbf::alloc_particle_arrays(Solver* hs, size_t n) {
   pbf_handle* h = static_cast<pbf_handle*>(hs);
   if (n + 1 <= h->cap) return PBF_OK;
   free_arrays(h);
-  const size_t cap = (n + 1 + 31) / 32 * 32;   // +1: the sentinel particle lives at index n_sorted
+  // +1: the sentinel particle lives at index n_sorted; +32: the neighbour build reads candidates in
+  // unconditional groups of 8 and may run past the last particle (masked off)
+  const size_t cap = (n + 1 + 31) / 32 * 32 + 32;
   for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
   CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
   CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap));

@@ -182,6 +182,28 @@ k_reorder(uint32_t n_upper, const uint32_t* __restrict__ n_sorted_ptr, const uin
 // exactly 0 to every sum).  Two passes over the 9 z-runs of candidates (count, then fill) — no
 // truncation, ever.
 // ------------------------------------------------------------------------------------------------
+// Single pass over the candidates: the predicate results are kept as bitmasks (one word per 32
+// candidates of a z-run, parked in thread-local memory: one store per 32 candidates), the counts
+// come from popc, rows are allocated with one atomic per slice, and the fill phase just walks
+// the set bits.  Candidates are evaluated in unconditional groups of 8 (reads past the end of a
+// run are in-bounds of the padded arrays and masked off), so the inner loop has no bounds checks.
+static constexpr int NB_MAXW = 6;       // cached words per z-run: 192 candidates in 3 cells (lattice: 81);
+                                        // longer runs (strong local compression) recompute their tail words
+
+__device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, float3 pi, float h2, uint32_t wb, uint32_t lim) {
+  uint32_t m = 0;
+  for (uint32_t g = 0; g < lim; g += 8) {
+    const float4* src = xs + wb + g;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const float4 q = __ldg(src + u);
+      m |= (ex_is_neighbor(pi, make_float3(q.x, q.y, q.z), h2) ? 1u : 0u) << (g + u);
+    }
+  }
+  if (lim < 32u) m &= (1u << lim) - 1u;
+  return m;
+}
+
 __global__ void __launch_bounds__(TPB)
 k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt_range, uint32_t sentinel,
                   const float4* __restrict__ xs,
@@ -192,36 +214,39 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
   const bool valid = t < cnt_range;
-  float3 pi = make_float3(0.f, 0.f, 0.f);
+  uint32_t masks[9 * NB_MAXW];
   uint32_t jb[9], je[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) { jb[k] = 0; je[k] = 0; }
+  uint32_t cnt = 0;
+  float3 pi = make_float3(0.f, 0.f, 0.f);
   if (valid) {
     pi = xyz(xs[i]);
     const int3 c = cell_coords(P, pi.x, pi.y, pi.z);
     const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, P.gdim[2] - 1);
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 9; k++) {
       const int cx = c.x + (k / 3) - 1, cy = c.y + (k % 3) - 1;
+      uint32_t b0 = 0, e0 = 0;
       if (cx >= 0 && cx < P.gdim[0] && cy >= 0 && cy < P.gdim[1]) {
         const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
-        jb[k] = cell_start[base + zlo];
-        je[k] = cell_start[base + zhi + 1];
+        b0 = cell_start[base + zlo];
+        e0 = cell_start[base + zhi + 1];
+      }
+      const uint32_t words = (e0 - b0 + 31u) >> 5;
+      jb[k] = b0; je[k] = e0;
+      for (uint32_t w = 0; w < words; w++) {
+        const uint32_t wb = b0 + 32u * w;
+        uint32_t m = nb_eval_word(xs, pi, P.h2, wb, min(32u, e0 - wb));
+        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));      // i lies in run 4 (own column) only
+        if (w < (uint32_t)NB_MAXW) masks[k * NB_MAXW + w] = m;
+        cnt += __popc(m);
       }
     }
   }
-  uint32_t cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 9; k++)
-    for (uint32_t j = jb[k]; j < je[k]; j++) {
-      const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
-      cnt += take ? 1u : 0u;
-    }
-  const uint32_t m = (__reduce_max_sync(0xffffffffu, cnt) + 3u) >> 2;    // rows of uint4
+  const uint32_t rows = (__reduce_max_sync(0xffffffffu, cnt) + 3u) >> 2;    // rows of uint4
   unsigned long long off = 0;
   if (lane == 0) {
-    off = atomicAdd(&sc->nbr_cursor, (unsigned long long)m);
-    if (off + m > cap_rows) { atomicOr(&sc->err, ERRBIT_NBR_CAPACITY); off = ~0ull; }
+    off = atomicAdd(&sc->nbr_cursor, (unsigned long long)rows);
+    if (off + rows > cap_rows) { atomicOr(&sc->err, ERRBIT_NBR_CAPACITY); off = ~0ull; }
   }
   off = __shfl_sync(0xffffffffu, off, 0);
   if (!valid) return;
@@ -230,12 +255,25 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   nbr_cnt[t] = cnt;
   uint32_t* out = nbr + off * 128ull + lane * 4;
   uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < 9; k++)
-    for (uint32_t j = jb[k]; j < je[k]; j++) {
-      const bool take = (j != i || include_self) && ex_is_neighbor(pi, xyz(__ldg(&xs[j])), P.h2);
-      if (take) { out[(size_t)(s >> 2) * 128u + (s & 3u)] = j; s++; }
+#pragma unroll 1
+  for (int k = 0; k < 9; k++) {
+    const uint32_t words = (je[k] - jb[k] + 31u) >> 5;
+    for (uint32_t w = 0; w < words; w++) {
+      const uint32_t wb = jb[k] + 32u * w;
+      uint32_t m;
+      if (w < (uint32_t)NB_MAXW) m = masks[k * NB_MAXW + w];
+      else {                                                             // rare: crowded run, recompute
+        m = nb_eval_word(xs, pi, P.h2, wb, min(32u, je[k] - wb));
+        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));
+      }
+      while (m) {
+        const uint32_t b = __ffs(m) - 1;
+        m &= m - 1;
+        out[(size_t)(s >> 2) * 128u + (s & 3u)] = wb + b;
+        s++;
+      }
     }
+  }
   for (; s & 3u; s++) out[(size_t)(s >> 2) * 128u + (s & 3u)] = sentinel;   // sentinel padding
 }
 

@@ -276,3 +276,33 @@ def test_large_block_properties():
     P64, _, _ = o64.download()
     floor = np.percentile(np.linalg.norm(Po - P64, axis=1), 50)
     _gate_whole_step("24^3 block", Pg, Rg, Po, Ro, 700.0, p50_gate=max(1e-5, floor))
+
+
+def test_crowded_cells_neighbor_sets(monkeypatch):
+    """Strong local compression: several hundred particles in a few cells, so that a z-run of 3
+    cells holds more candidates than the neighbour build caches (6 words = 192): the tail words are
+    recomputed.  Neighbour sets must still equal the fp32 oracle's exactly."""
+    monkeypatch.setenv("PBF_NBR_ROWS", "256")       # room for ~1000 neighbours per particle
+    rng = np.random.default_rng(3)
+    pos = np.concatenate([rng.uniform(-0.25, 0.25, size=(900, 3)) + [0.0, 0.6, 0.0],
+                          rng.uniform(-0.9, 0.9, size=(300, 3)) * [1, 0.3, 1] + [0.0, 0.5, 0.0]])
+    vel = rng.normal(0, 0.2, size=pos.shape)
+    g = _gpu(700.0, iterations=0); g.upload(pos, vel); g.step(1)
+    o = _oracle(700.0, 32, iterations=0); o.upload(pos, vel); o.step(1)
+    dg, cg = g.neighbor_digest(); do, co = o.digest()
+    assert cg.max() > 400
+    assert np.array_equal(cg, co) and np.array_equal(dg, do)
+    rg, colg = g.neighbors(); ro, colo = o.neighbors()
+    assert np.array_equal(rg, ro) and np.array_equal(colg, colo)
+
+
+def test_neighbor_capacity_overflow_is_loud(monkeypatch):
+    """Lists are never truncated: running out of rows is PBF_ERR_CAPACITY."""
+    from fluid_b200 import api
+    monkeypatch.setenv("PBF_NBR_ROWS", "4")
+    rng = np.random.default_rng(4)
+    pos = rng.uniform(-0.2, 0.2, size=(500, 3)) + [0.0, 0.6, 0.0]
+    g = _gpu(700.0, iterations=0); g.upload(pos, np.zeros_like(pos))
+    with pytest.raises(api.PbfError) as e:
+        g.step(1)
+    assert e.value.code == api.PBF_ERR_CAPACITY
