@@ -57,6 +57,8 @@ def load_library():
         "pbf_upload": (i32, [vp, sz, vp, vp]),
         "pbf_download": (i32, [vp, vp, vp, vp]),
         "pbf_num_particles": (sz, [vp]),
+        "pbf_host_register": (i32, [vp, vp, sz]),
+        "pbf_host_unregister": (i32, [vp, vp]),
         "pbf_step": (i32, [vp, i32]),
         "pbf_sync": (i32, [vp]),
         "pbf_estimate_densities": (i32, [vp]),
@@ -125,6 +127,16 @@ class Solver:
         assert pos.shape == vel.shape and (pos.size == 0 or pos.shape[1] == 3)
         self.n = pos.shape[0]
         self._ck(self.lib.pbf_upload(self.h, self.n, _ptr(pos), _ptr(vel)))
+
+    def pin(self, *arrays):
+        """Page-lock numpy arrays the caller will reuse for upload()/download_into() (pbf_host_register)."""
+        for a in arrays:
+            assert a.flags["C_CONTIGUOUS"]
+            self._ck(self.lib.pbf_host_register(self.h, _ptr(a), a.nbytes))
+
+    def unpin(self, *arrays):
+        for a in arrays:
+            self._ck(self.lib.pbf_host_unregister(self.h, _ptr(a)))
 
     def upload_device(self, n, d_pos_ptr, d_vel_ptr):
         self.n = n

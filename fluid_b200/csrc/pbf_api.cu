@@ -157,7 +157,26 @@ int pbf::sync_and_check(Solver* hs) {
 }
 
 // pinned staging lives outside the struct so pbf_internal.h stays CUDA-only
-struct HandleExtra { PinnedBuf pin; };
+struct HostRange { char* p; size_t bytes; };
+struct HandleExtra {
+  PinnedBuf pin;
+  std::vector<HostRange> regs;       // caller buffers page-locked through pbf_host_register
+  double* stage64 = nullptr; size_t stage64_cap = 0;   // device staging for fp64 AoS (7 doubles / particle)
+  bool registered(const void* q, size_t bytes) const {
+    const char* c = (const char*)q;
+    for (const HostRange& r : regs) if (c >= r.p && c + bytes <= r.p + r.bytes) return true;
+    return false;
+  }
+  ~HandleExtra() { for (HostRange& r : regs) cudaHostUnregister(r.p); if (stage64) cudaFree(stage64); }
+  cudaError_t ensure_stage64(size_t n) {
+    if (n <= stage64_cap) return cudaSuccess;
+    if (stage64) cudaFree(stage64);
+    stage64 = nullptr; stage64_cap = 0;
+    cudaError_t e = cudaMalloc((void**)&stage64, n * sizeof(double));
+    if (e == cudaSuccess) stage64_cap = n;
+    return e;
+  }
+};
 static HandleExtra* extra_of(pbf_handle* h);
 
 #include <map>
@@ -251,13 +270,21 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   if (n == 0) return PBF_OK;
   HandleExtra* x = extra_of(h);
-  CK(h, x->pin.ensure(6 * n));
-  float* st = x->pin.p;
-  parallel_for(3 * n, [&](size_t a, size_t b) {
-    for (size_t i = a; i < b; i++) { st[i] = (float)pos_xyz[i]; st[3 * n + i] = (float)vel_xyz[i]; }
-  });
-  CK(h, cudaMemcpyAsync(h->io_stage, st, 6 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  enqueue_import(h, h->io_stage, h->io_stage + 3 * n);
+  if (x->registered(pos_xyz, 3 * n * sizeof(double)) && x->registered(vel_xyz, 3 * n * sizeof(double))) {
+    // page-locked caller buffers: DMA the doubles as they are, convert on the device
+    CK(h, x->ensure_stage64(7 * h->cap));
+    CK(h, cudaMemcpyAsync(x->stage64, pos_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(x->stage64 + 3 * n, vel_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    enqueue_import_f64(h, x->stage64, x->stage64 + 3 * n);
+  } else {
+    CK(h, x->pin.ensure(6 * n));
+    float* st = x->pin.p;
+    parallel_for(3 * n, [&](size_t a, size_t b) {
+      for (size_t i = a; i < b; i++) { st[i] = (float)pos_xyz[i]; st[3 * n + i] = (float)vel_xyz[i]; }
+    });
+    CK(h, cudaMemcpyAsync(h->io_stage, st, 6 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    enqueue_import(h, h->io_stage, h->io_stage + 3 * n);
+  }
   CK(h, cudaStreamSynchronize(h->stream));
   CK(h, cudaGetLastError());
   return PBF_OK;
@@ -331,6 +358,16 @@ int pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* densit
   if (n == 0) return pbf_sync(h);
   CK(h, cudaSetDevice(h->device));
   HandleExtra* x = extra_of(h);
+  if ((!pos_xyz || x->registered(pos_xyz, 3 * n * sizeof(double))) && (!vel_xyz || x->registered(vel_xyz, 3 * n * sizeof(double))) &&
+      (!density || x->registered(density, n * sizeof(double)))) {
+    // page-locked caller buffers: scatter to original order as fp64 on the device, DMA straight out
+    CK(h, x->ensure_stage64(7 * h->cap));
+    double* d64 = x->stage64;
+    if (pos_xyz) { enqueue_export3_f64(h, h->pos[h->cur], d64); CK(h, cudaMemcpyAsync(pos_xyz, d64, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    if (vel_xyz) { enqueue_export3_f64(h, h->vel[h->cur], d64 + 3 * n); CK(h, cudaMemcpyAsync(vel_xyz, d64 + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    if (density) { enqueue_export1_f64(h, h->rho, d64 + 6 * n); CK(h, cudaMemcpyAsync(density, d64 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    return pbf_sync(h);
+  }
   CK(h, x->pin.ensure(7 * n));
   float* st = x->pin.p;
   float* d = h->io_stage;
@@ -345,6 +382,26 @@ int pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* densit
   });
   if (density) parallel_for(n, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) density[i] = (double)st[6 * n + i]; });
   return PBF_OK;
+}
+
+// Page-lock caller-owned host buffers (cudaHostRegister) so that pbf_upload / pbf_download can DMA
+// to and from them directly.  The caller must unregister (or destroy the handle) before freeing.
+int pbf_host_register(pbf_handle* h, void* ptr, size_t bytes) {
+  if (!h || !ptr || !bytes) return PBF_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  HandleExtra* x = extra_of(h);
+  if (x->registered(ptr, bytes)) return PBF_OK;
+  CK(h, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  x->regs.push_back(HostRange{(char*)ptr, bytes});
+  return PBF_OK;
+}
+
+int pbf_host_unregister(pbf_handle* h, void* ptr) {
+  if (!h || !ptr) return PBF_ERR_INVALID;
+  HandleExtra* x = extra_of(h);
+  for (size_t k = 0; k < x->regs.size(); k++)
+    if (x->regs[k].p == (char*)ptr) { cudaHostUnregister(ptr); x->regs.erase(x->regs.begin() + k); return PBF_OK; }
+  return fail(h, PBF_ERR_INVALID, "pbf_host_unregister: pointer was not registered");
 }
 
 // ---- parity / debug ---------------------------------------------------------------------------

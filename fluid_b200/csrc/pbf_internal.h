@@ -112,6 +112,9 @@ void enqueue_export3(Solver* h, const float4* src, float* dst_xyz);
 void enqueue_export1(Solver* h, const float* src, float* dst);
 void enqueue_export_w(Solver* h, const float4* src, float* dst);
 void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count);
+void enqueue_import_f64(Solver* h, const double* d_pos_xyz, const double* d_vel_xyz);
+void enqueue_export3_f64(Solver* h, const float4* src, double* dst_xyz);
+void enqueue_export1_f64(Solver* h, const float* src, double* dst);
 
 }  // namespace pbf
 

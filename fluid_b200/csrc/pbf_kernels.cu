@@ -194,11 +194,13 @@ __device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, 
   uint32_t m = 0;
   for (uint32_t g = 0; g < lim; g += 8) {
     const float4* src = xs + wb + g;
+    uint32_t m8 = 0;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const float4 q = __ldg(src + u);
-      m |= (ex_is_neighbor(pi, make_float3(q.x, q.y, q.z), h2) ? 1u : 0u) << (g + u);
+      if (ex_is_neighbor(pi, make_float3(q.x, q.y, q.z), h2)) m8 |= (1u << u);   // predicated OR with an immediate
     }
+    m |= m8 << g;
   }
   if (lim < 32u) m &= (1u << lim) - 1u;
   return m;
@@ -511,6 +513,31 @@ k_import(uint32_t n, const float* __restrict__ pos_xyz, const float* __restrict_
   orig[i] = i;
 }
 
+// fp64 host layout converted on the device (same round-to-nearest cast as the host path)
+__global__ void __launch_bounds__(TPB)
+k_import_f64(uint32_t n, const double* __restrict__ pos_xyz, const double* __restrict__ vel_xyz,
+             float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ orig) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  pos[i] = make_float4((float)pos_xyz[3 * i], (float)pos_xyz[3 * i + 1], (float)pos_xyz[3 * i + 2], 0.f);
+  vel[i] = make_float4((float)vel_xyz[3 * i], (float)vel_xyz[3 * i + 1], (float)vel_xyz[3 * i + 2], 0.f);
+  orig[i] = i;
+}
+__global__ void __launch_bounds__(TPB)
+k_export3_f64(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict__ orig, double* __restrict__ dst_xyz) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  const float4 v = src[s];
+  const size_t o = orig ? orig[s] : s;
+  dst_xyz[3 * o] = (double)v.x; dst_xyz[3 * o + 1] = (double)v.y; dst_xyz[3 * o + 2] = (double)v.z;
+}
+__global__ void __launch_bounds__(TPB)
+k_export1_f64(uint32_t n, const float* __restrict__ src, const uint32_t* __restrict__ orig, double* __restrict__ dst) {
+  const uint32_t s = blockIdx.x * TPB + threadIdx.x;
+  if (s >= n) return;
+  dst[orig ? orig[s] : s] = (double)src[s];
+}
+
 __global__ void __launch_bounds__(TPB)
 k_export3(uint32_t n, const float4* __restrict__ src, const uint32_t* __restrict__ orig, float* __restrict__ dst_xyz) {
   const uint32_t s = blockIdx.x * TPB + threadIdx.x;
@@ -656,6 +683,18 @@ void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;
   LAUNCH(h, K_IO, k_import, blocks_for(n), n, d_pos_xyz, d_vel_xyz, h->pos[h->cur], h->vel[h->cur], h->orig[h->cur]);
+}
+
+void enqueue_import_f64(Solver* h, const double* d_pos_xyz, const double* d_vel_xyz) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n == 0) return;
+  LAUNCH(h, K_IO, k_import_f64, blocks_for(n), n, d_pos_xyz, d_vel_xyz, h->pos[h->cur], h->vel[h->cur], h->orig[h->cur]);
+}
+void enqueue_export3_f64(Solver* h, const float4* src, double* dst_xyz) {
+  if (h->r_cnt) LAUNCH(h, K_IO, k_export3_f64, blocks_for(h->r_cnt), h->r_cnt, src + h->r_i0, h->slab ? (const uint32_t*)nullptr : h->orig[h->cur] + h->r_i0, dst_xyz);
+}
+void enqueue_export1_f64(Solver* h, const float* src, double* dst) {
+  if (h->r_cnt) LAUNCH(h, K_IO, k_export1_f64, blocks_for(h->r_cnt), h->r_cnt, src + h->r_i0, h->slab ? (const uint32_t*)nullptr : h->orig[h->cur] + h->r_i0, dst);
 }
 
 // exports act on the owned range; dst index = original id (single GPU) or position in the range (slab)

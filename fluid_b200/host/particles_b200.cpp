@@ -43,6 +43,9 @@ void Particles::ensureUploaded() {
     pos_[3*i] = ps[i]->position.x; pos_[3*i+1] = ps[i]->position.y; pos_[3*i+2] = ps[i]->position.z;
     vel_[3*i] = ps[i]->velocity.x; vel_[3*i+1] = ps[i]->velocity.y; vel_[3*i+2] = ps[i]->velocity.z;
   }
+  // the mirror arrays live as long as the handle: page-lock them once so every step's read-back is a direct DMA
+  if (n) { pbf_host_register(handle_, pos_.data(), 3 * n * sizeof(double)); pbf_host_register(handle_, vel_.data(), 3 * n * sizeof(double));
+           pbf_host_register(handle_, rho_.data(), n * sizeof(double)); }
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   uploaded_ = true;

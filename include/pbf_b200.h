@@ -79,6 +79,10 @@ int  pbf_device_count(void);                    /* 0 when no CUDA device is visi
 int  pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz);
 int  pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density); /* syncs; any pointer may be NULL */
 size_t pbf_num_particles(pbf_handle* h);
+/* Optional: page-lock caller-owned host buffers so upload/download DMA them directly (fp64 on the
+ * wire, conversion on the device).  Unregister, or destroy the handle, before freeing them. */
+int  pbf_host_register(pbf_handle* h, void* ptr, size_t bytes);
+int  pbf_host_unregister(pbf_handle* h, void* ptr);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 int  pbf_step(pbf_handle* h, int n_steps);      /* enqueues n_steps * timeStep(dt); asynchronous */

@@ -306,3 +306,20 @@ def test_neighbor_capacity_overflow_is_loud(monkeypatch):
     with pytest.raises(api.PbfError) as e:
         g.step(1)
     assert e.value.code == api.PBF_ERR_CAPACITY
+
+
+def test_page_locked_io_path_is_bit_identical():
+    """pbf_host_register: fp64 on the wire + conversion on the device gives the same bits as the
+    staged host-conversion path, for upload and download."""
+    pos, vel, rho0, _ = _scene("two_blocks")
+    g1 = _gpu(rho0); g1.upload(pos, vel); g1.step(2); ref = g1.download()
+    g2 = _gpu(rho0)
+    P = np.ascontiguousarray(pos.copy()); V = np.ascontiguousarray(vel.copy()); R = np.empty(len(pos))
+    g2.pin(P, V, R)
+    g2.upload(P, V); g2.step(1)
+    g2.download_into(P, V, R)             # read back ...
+    g2.upload(P, V); g2.step(1)           # ... and re-upload through the pinned path: state survives exactly? no: velocities do, see below
+    g2.download_into(P, V, R)
+    # a download/upload round trip is lossless (fp32 -> fp64 -> fp32), so two single steps == one 2-step call
+    assert np.array_equal(P, ref[0]) and np.array_equal(V, ref[1]) and np.array_equal(R, ref[2])
+    g2.unpin(P, V, R)
