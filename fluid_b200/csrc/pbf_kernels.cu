@@ -187,8 +187,8 @@ k_reorder(uint32_t n_upper, const uint32_t* __restrict__ n_sorted_ptr, const uin
 // come from popc, rows are allocated with one atomic per slice, and the fill phase just walks
 // the set bits.  Candidates are evaluated in unconditional groups of 8 (reads past the end of a
 // run are in-bounds of the padded arrays and masked off), so the inner loop has no bounds checks.
-static constexpr int NB_MAXW = 6;       // cached words per z-run: 192 candidates in 3 cells (lattice: 81);
-                                        // longer runs (strong local compression) recompute their tail words
+static constexpr int NB_TOTW = 48;      // cached mask words per particle (a lattice at spacing h/3 needs 27);
+                                        // crowded neighbourhoods recompute the words beyond that in the fill phase
 
 __device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, float3 pi, float h2, uint32_t wb, uint32_t lim) {
   uint32_t m = 0;
@@ -206,6 +206,34 @@ __device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, 
   return m;
 }
 
+// Candidate range [b, e) of z-run k (k = 3*(dx+1) + (dy+1)) for a particle at pi in cell c, with
+// conservative culling: the run is dropped when the (dx,dy) cell column is farther than h in the
+// xy-plane, and its z-extent is trimmed to the cells that can still reach the particle.  `slack`
+// covers the fp32 rounding of the cell assignment (a particle may sit a few ulp outside the
+// nominal bounds of its cell), so no true neighbour is ever culled; the exact predicate decides.
+__device__ __forceinline__ void nb_run_range(const DevParams& P, const uint32_t* __restrict__ cell_start, float3 pi, int3 c, int k,
+                                             float cell, uint32_t& b, uint32_t& e) {
+  b = 0; e = 0;
+  const int ox = (k / 3) - 1, oy = (k % 3) - 1;
+  const int cx = c.x + ox, cy = c.y + oy;
+  if (cx < 0 || cx >= P.gdim[0] || cy < 0 || cy >= P.gdim[1]) return;
+  const float slack = 1e-3f * P.h + 1e-6f * fmaxf(fabsf(pi.x), fmaxf(fabsf(pi.y), fabsf(pi.z)));
+  // distance from the particle to the neighbouring column along x and y (0 for the own column)
+  const float x_lo = P.gmin[0] + (float)(c.x + P.cx_offset) * cell, y_lo = P.gmin[1] + (float)c.y * cell;
+  float dx = ox < 0 ? pi.x - x_lo : (ox > 0 ? (x_lo + cell) - pi.x : 0.f);
+  float dy = oy < 0 ? pi.y - y_lo : (oy > 0 ? (y_lo + cell) - pi.y : 0.f);
+  dx = fmaxf(dx - slack, 0.f); dy = fmaxf(dy - slack, 0.f);
+  const float rz2 = P.h2 - (dx * dx + dy * dy);
+  if (rz2 < 0.f) return;
+  const float z_lo = P.gmin[2] + (float)c.z * cell;
+  const float dzl = fmaxf(pi.z - z_lo - slack, 0.f), dzh = fmaxf((z_lo + cell) - pi.z - slack, 0.f);
+  const int zlo = (c.z > 0 && dzl * dzl <= rz2) ? c.z - 1 : c.z;
+  const int zhi = (c.z < P.gdim[2] - 1 && dzh * dzh <= rz2) ? c.z + 1 : c.z;
+  const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
+  b = cell_start[base + zlo];
+  e = cell_start[base + zhi + 1];
+}
+
 __global__ void __launch_bounds__(TPB)
 k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt_range, uint32_t sentinel,
                   const float4* __restrict__ xs,
@@ -216,31 +244,24 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
   const bool valid = t < cnt_range;
-  uint32_t masks[9 * NB_MAXW];
-  uint32_t jb[9], je[9];
-  uint32_t cnt = 0;
+  uint32_t masks[NB_TOTW], wbase[NB_TOTW];
+  uint32_t cnt = 0, nwords = 0, cnt_cached = 0;
   float3 pi = make_float3(0.f, 0.f, 0.f);
+  int3 c = make_int3(0, 0, 0);
+  const float cell = 1.0f / P.inv_cell;
   if (valid) {
     pi = xyz(xs[i]);
-    const int3 c = cell_coords(P, pi.x, pi.y, pi.z);
-    const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, P.gdim[2] - 1);
+    c = cell_coords(P, pi.x, pi.y, pi.z);
 #pragma unroll 1
     for (int k = 0; k < 9; k++) {
-      const int cx = c.x + (k / 3) - 1, cy = c.y + (k % 3) - 1;
-      uint32_t b0 = 0, e0 = 0;
-      if (cx >= 0 && cx < P.gdim[0] && cy >= 0 && cy < P.gdim[1]) {
-        const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
-        b0 = cell_start[base + zlo];
-        e0 = cell_start[base + zhi + 1];
-      }
-      const uint32_t words = (e0 - b0 + 31u) >> 5;
-      jb[k] = b0; je[k] = e0;
-      for (uint32_t w = 0; w < words; w++) {
-        const uint32_t wb = b0 + 32u * w;
+      uint32_t b0, e0;
+      nb_run_range(P, cell_start, pi, c, k, cell, b0, e0);
+      for (uint32_t wb = b0; wb < e0; wb += 32u) {
         uint32_t m = nb_eval_word(xs, pi, P.h2, wb, min(32u, e0 - wb));
-        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));      // i lies in run 4 (own column) only
-        if (w < (uint32_t)NB_MAXW) masks[k * NB_MAXW + w] = m;
+        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));      // only the own column's run contains i
         cnt += __popc(m);
+        if (nwords < (uint32_t)NB_TOTW) { masks[nwords] = m; wbase[nwords] = wb; cnt_cached = cnt; }
+        nwords++;
       }
     }
   }
@@ -256,23 +277,30 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   if (lane == 0) slice_off[t >> 5] = (uint32_t)off;
   nbr_cnt[t] = cnt;
   uint32_t* out = nbr + off * 128ull + lane * 4;
-  uint32_t s = 0;
+  // fill: one flat loop over the set bits of the cached words (trip count = this lane's count)
+  uint32_t s = 0, wi = 0, m = 0, wb = 0;
+  for (; s < cnt_cached; s++) {
+    while (m == 0) { m = masks[wi]; wb = wbase[wi]; wi++; }
+    const uint32_t bit = __ffs(m) - 1;
+    m &= m - 1;
+    out[(size_t)(s >> 2) * 128u + (s & 3u)] = wb + bit;
+  }
+  if (nwords > (uint32_t)NB_TOTW) {                        // rare: recompute the words that did not fit
+    uint32_t widx = 0;
 #pragma unroll 1
-  for (int k = 0; k < 9; k++) {
-    const uint32_t words = (je[k] - jb[k] + 31u) >> 5;
-    for (uint32_t w = 0; w < words; w++) {
-      const uint32_t wb = jb[k] + 32u * w;
-      uint32_t m;
-      if (w < (uint32_t)NB_MAXW) m = masks[k * NB_MAXW + w];
-      else {                                                             // rare: crowded run, recompute
-        m = nb_eval_word(xs, pi, P.h2, wb, min(32u, je[k] - wb));
-        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));
-      }
-      while (m) {
-        const uint32_t b = __ffs(m) - 1;
-        m &= m - 1;
-        out[(size_t)(s >> 2) * 128u + (s & 3u)] = wb + b;
-        s++;
+    for (int k = 0; k < 9; k++) {
+      uint32_t b0, e0;
+      nb_run_range(P, cell_start, pi, c, k, cell, b0, e0);
+      for (uint32_t w0 = b0; w0 < e0; w0 += 32u, widx++) {
+        if (widx < (uint32_t)NB_TOTW) continue;
+        uint32_t mm = nb_eval_word(xs, pi, P.h2, w0, min(32u, e0 - w0));
+        if (!include_self && i - w0 < 32u) mm &= ~(1u << (i - w0));
+        while (mm) {
+          const uint32_t bit = __ffs(mm) - 1;
+          mm &= mm - 1;
+          out[(size_t)(s >> 2) * 128u + (s & 3u)] = w0 + bit;
+          s++;
+        }
       }
     }
   }
@@ -280,10 +308,11 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
 }
 
 // the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
-__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* vtmp, float4* omega) {
+__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     a[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     b[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    w[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     vtmp[n] = make_float4(0.f, 0.f, 0.f, 0.f);
     omega[n] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -401,7 +430,7 @@ k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __rest
 
 __global__ void __launch_bounds__(TPB)
 k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
-                 const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
+                 float4* __restrict__ xs_w, const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
                  double* __restrict__ rho_sum) {
@@ -430,7 +459,9 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
 #undef BODY_V
     rho = P.poly6_c * w3s;
     ox *= P.spiky_c; oy *= P.spiky_c; oz *= P.spiky_c;
-    omega[i] = make_float4(ox, oy, oz, sqrtf(ox * ox + oy * oy + oz * oz));
+    const float on = sqrtf(ox * ox + oy * oy + oz * oz);
+    omega[i] = make_float4(ox, oy, oz, on);
+    xs_w[i] = make_float4(pi.x, pi.y, pi.z, on);        // (x*, |omega|): ONE 16-byte gather per pair in the confinement pass
     const float xc = P.enable_xsph ? P.visc_c * P.poly6_c : 0.f;   // v += C * sum v_ij W  (not density-normalised, Q12)
     vel_out[i] = make_float4(fmaf(xc, sx, vi.x), fmaf(xc, sy, vi.y), fmaf(xc, sz, vi.z), 0.f);
     rho_out[i] = rho;                                              // the density the visualiser reads
@@ -439,7 +470,7 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
 }
 
 __global__ void __launch_bounds__(TPB)
-k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
+k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs /* (x*, |omega|) */,
                  const float4* __restrict__ omega, float4* __restrict__ vel, float4* __restrict__ pos,
                  const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
                  const uint32_t* __restrict__ nbr_cnt) {
@@ -452,11 +483,10 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
 #define BODY_C(J)                                                          \
     {                                                                      \
       const float4 pj = __ldg(&xs[J]);                                     \
-      const float wn = __ldg(&omega[J].w);                                 \
       const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;    \
       float r2, w3, g;                                                     \
       pair_terms(P, dx, dy, dz, r2, w3, g);                                \
-      const float f = wn * g;      /* |omega_j| * grad W (no own term, Q13) */ \
+      const float f = pj.w * g;    /* |omega_j| * grad W (no own term, Q13) */ \
       ex = fmaf(f, dx, ex); ey = fmaf(f, dy, ey); ez = fmaf(f, dz, ez);    \
     }
     PBF_FOR_NEIGHBORS(t, BODY_C)
@@ -625,7 +655,7 @@ void enqueue_sort(Solver* h, size_t n_in) {
 // Phase 3: frozen neighbour lists for the range [r_i0, r_i0 + r_cnt) of the n_sorted sorted particles.
 void enqueue_build(Solver* h, int include_self) {
   h->prof_begin(K_REORDER);
-  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->vtmp, h->omega);
+  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega);
   h->prof_end(K_REORDER); h->launches++;
   LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
          h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
@@ -644,11 +674,11 @@ void enqueue_velocity(Solver* h) {   // every sorted particle, ghosts included (
   LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp);
 }
 void enqueue_vorticity(Solver* h) {
-  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->vtmp, h->vel[h->cur], h->omega,
+  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->xs_tmp, h->vtmp, h->vel[h->cur], h->omega,
          h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
 }
 void enqueue_confine(Solver* h) {
-  LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->omega, h->vel[h->cur],
+  LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
          h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt);
 }
 

@@ -372,6 +372,7 @@ void* pbf_slab_buffer(pbf_handle* h, int which, size_t* bytes_out) {
     case PBF_BUF_XS_A: p = h->xs_a; b = arr; break;
     case PBF_BUF_XS_B: p = h->xs_b; b = arr; break;
     case PBF_BUF_OMEGA: p = h->omega; b = arr; break;
+    case PBF_BUF_XS_W: p = h->xs_tmp; b = arr; break;
     default: break;
   }
   if (bytes_out) *bytes_out = b;

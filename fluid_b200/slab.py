@@ -18,7 +18,7 @@ import numpy as np
 from . import api
 
 (BUF_MIG_SEND_L, BUF_MIG_SEND_R, BUF_MIG_RECV_L, BUF_MIG_RECV_R, BUF_GHOST_SEND_L, BUF_GHOST_SEND_R,
- BUF_GHOST_RECV_L, BUF_GHOST_RECV_R, BUF_XS_A, BUF_XS_B, BUF_OMEGA) = range(11)
+ BUF_GHOST_RECV_L, BUF_GHOST_RECV_R, BUF_XS_A, BUF_XS_B, BUF_OMEGA, BUF_XS_W) = range(12)
 PH_LAMBDA_FIRST, PH_LAMBDA, PH_DELTA, PH_VELOCITY, PH_VORTICITY, PH_CONFINE = range(6)
 
 
@@ -188,7 +188,7 @@ class SlabSolver:
     def _map_buffers(self):
         torch = self.torch
         self.buf = {}
-        for which in range(11):
+        for which in range(12):
             nbytes = C.c_size_t()
             ptr = self.lib.pbf_slab_buffer(self.h, which, C.byref(nbytes))
             t = torch.as_tensor(_DevMem(ptr, nbytes.value // 4), device=f"cuda:{self.device}")
@@ -220,7 +220,7 @@ class SlabSolver:
             self._halo(BUF_XS_A)
         self._ck(lib.pbf_slab_phase(h, PH_VELOCITY))
         self._ck(lib.pbf_slab_phase(h, PH_VORTICITY))
-        self._halo(BUF_OMEGA)
+        self._halo(BUF_XS_W)          # ghost (x*, |omega|): the confinement pass gathers one float4 per pair
         self._ck(lib.pbf_slab_phase(h, PH_CONFINE))
 
     def step(self, n_steps=1):

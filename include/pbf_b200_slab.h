@@ -23,7 +23,7 @@
  *   pbf_slab_phase_sort      append ghosts, counting sort, neighbour lists; returns b0..b3,n (syncs)
  *   iterations x { pbf_slab_phase(LAMBDA) ; <copy XS_B[b0,b1) -> left's XS_B[b3',n'), XS_B[b2,b3) -> right's XS_B[0,b0')> ;
  *                  pbf_slab_phase(DELTA)  ; <same for XS_A> }
- *   pbf_slab_phase(VELOCITY) ; pbf_slab_phase(VORTICITY) ; <same copy for OMEGA> ; pbf_slab_phase(CONFINE)
+ *   pbf_slab_phase(VELOCITY) ; pbf_slab_phase(VORTICITY) ; <same copy for XS_W = (x*,|omega|)> ; pbf_slab_phase(CONFINE)
  */
 #ifndef PBF_B200_SLAB_H
 #define PBF_B200_SLAB_H
@@ -67,7 +67,8 @@ int pbf_slab_stats(pbf_handle* h, double* rho_first_sum, double* rho_final_sum, 
  * bits), then 3 float4 per migrant (x|id, x*, v) or 2 per ghost (x*|id, x). */
 enum { PBF_BUF_MIG_SEND_L = 0, PBF_BUF_MIG_SEND_R = 1, PBF_BUF_MIG_RECV_L = 2, PBF_BUF_MIG_RECV_R = 3,
        PBF_BUF_GHOST_SEND_L = 4, PBF_BUF_GHOST_SEND_R = 5, PBF_BUF_GHOST_RECV_L = 6, PBF_BUF_GHOST_RECV_R = 7,
-       PBF_BUF_XS_A = 8, PBF_BUF_XS_B = 9, PBF_BUF_OMEGA = 10 };
+       PBF_BUF_XS_A = 8, PBF_BUF_XS_B = 9, PBF_BUF_OMEGA = 10,
+       PBF_BUF_XS_W = 11 /* (x*, |omega|) written by the vorticity pass, gathered by confinement */ };
 void* pbf_slab_buffer(pbf_handle* h, int which, size_t* bytes_out);
 
 #ifdef __cplusplus
