@@ -31,7 +31,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL banners off stdout: rank 0 prints ONE JSON line
 
 import numpy as np
 
@@ -189,6 +188,10 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    # NCCL / driver banners must not pollute stdout: rank 0 prints exactly ONE JSON line there
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -295,17 +298,20 @@ def main():
                 solver.upload(P, V); solver.step(1, sync=False); solver.download_into(P, V, R)
             torch.cuda.synchronize(); e_ms = (time.perf_counter() - t0) * 1e3
         else:
-            P, V, R = solver.download_local()
+            capn = int(solver.particle_cap)
+            P = np.empty((capn, 3)); V = np.empty((capn, 3)); R = np.empty(capn); I = np.empty(capn, dtype=np.uint32)
+            solver.pin(P, V, R)
+            nl = solver.download_local_into(P, V, R, I)
             barrier(); t0 = time.perf_counter()
             for _ in range(k2):
-                solver.upload_local(P, V, ids=solver.local_ids()); solver.step(1); P, V, R = solver.download_local()
+                solver.upload_local(P[:nl], V[:nl], ids=I[:nl]); solver.step(1); nl = solver.download_local_into(P, V, R, I)
             torch.cuda.synchronize(); e_ms = (time.perf_counter() - t0) * 1e3
         t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t[0])
         e2e = {"value": n_total * iters * k2 / (e_ms * 1e-3), "unit": "particle-iteration updates/s", "steps": k2,
-               "h2d_bytes_per_step": n_total * 6 * (8 if world == 1 else 4), "d2h_bytes_per_step": n_total * 7 * (8 if world == 1 else 4), "ms_per_step": e_ms / k2,
+               "h2d_bytes_per_step": n_total * (6 * 8 + (4 if world > 1 else 0)), "d2h_bytes_per_step": n_total * (7 * 8 + (4 if world > 1 else 0)), "ms_per_step": e_ms / k2,
                "note": "host fp64 AoS buffers (pos, vel) uploaded and (pos, vel, density) read back EVERY step via pbf_upload/pbf_step/pbf_download "
                        "(page-locked caller buffers, fp64 on the wire, fp64<->fp32 on the device); wall clock"}
 
@@ -322,7 +328,10 @@ def main():
                            "parallelism": "single GPU" if world == 1 else f"{world} x-slabs, NCCL halo exchange"},
                 "wall_ms_per_step": wall_ms / args.steps, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 

@@ -259,15 +259,11 @@ const char* pbf_last_error(pbf_handle* h) { return h ? h->last_error.c_str() : "
 size_t pbf_num_particles(pbf_handle* h) { return h ? h->n : 0; }
 uint64_t pbf_launch_count(pbf_handle* h) { return h ? h->launches : 0; }
 
-int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz) {
-  if (!h || (n && (!pos_xyz || !vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload: null argument");
-  if (n > 0xFFFFFFF0ull) return fail(h, PBF_ERR_INVALID, "pbf_upload: more than 2^32 particles");
-  CK(h, cudaSetDevice(h->device));
-  int rc = ensure_capacity(h, n);
-  if (rc != PBF_OK) return rc;
-  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
-  h->n = n; h->cur = 0; h->have_neighbors = false;
-  h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
+}  // extern "C" (reopened below)
+
+// host fp64 AoS -> pos/vel[cur] (orig = identity), page-locked fast path when the buffers are registered
+int pbf::io_upload(Solver* hs, size_t n, const double* pos_xyz, const double* vel_xyz) {
+  pbf_handle* h = static_cast<pbf_handle*>(hs);
   if (n == 0) return PBF_OK;
   HandleExtra* x = extra_of(h);
   if (x->registered(pos_xyz, 3 * n * sizeof(double)) && x->registered(vel_xyz, 3 * n * sizeof(double))) {
@@ -288,6 +284,52 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   CK(h, cudaStreamSynchronize(h->stream));
   CK(h, cudaGetLastError());
   return PBF_OK;
+}
+
+// owned range of pos/vel[cur] and rho -> host fp64 AoS (original order, or range order in slab mode)
+int pbf::io_download(Solver* hs, double* pos_xyz, double* vel_xyz, double* density) {
+  pbf_handle* h = static_cast<pbf_handle*>(hs);
+  const size_t n = h->r_cnt;
+  if (n == 0) return sync_and_check(h);
+  HandleExtra* x = extra_of(h);
+  if ((!pos_xyz || x->registered(pos_xyz, 3 * n * sizeof(double))) && (!vel_xyz || x->registered(vel_xyz, 3 * n * sizeof(double))) &&
+      (!density || x->registered(density, n * sizeof(double)))) {
+    // page-locked caller buffers: scatter to original order as fp64 on the device, DMA straight out
+    CK(h, x->ensure_stage64(7 * h->cap));
+    double* d64 = x->stage64;
+    if (pos_xyz) { enqueue_export3_f64(h, h->pos[h->cur], d64); CK(h, cudaMemcpyAsync(pos_xyz, d64, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    if (vel_xyz) { enqueue_export3_f64(h, h->vel[h->cur], d64 + 3 * n); CK(h, cudaMemcpyAsync(vel_xyz, d64 + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    if (density) { enqueue_export1_f64(h, h->rho, d64 + 6 * n); CK(h, cudaMemcpyAsync(density, d64 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
+    return sync_and_check(h);
+  }
+  CK(h, x->pin.ensure(7 * n));
+  float* st = x->pin.p;
+  float* d = h->io_stage;
+  if (pos_xyz) { enqueue_export3(h, h->pos[h->cur], d); CK(h, cudaMemcpyAsync(st, d, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  if (vel_xyz) { enqueue_export3(h, h->vel[h->cur], d + 3 * n); CK(h, cudaMemcpyAsync(st + 3 * n, d + 3 * n, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  if (density) { enqueue_export1(h, h->rho, d + 6 * n); CK(h, cudaMemcpyAsync(st + 6 * n, d + 6 * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
+  int rc = sync_and_check(h);
+  if (rc != PBF_OK) return rc;
+  parallel_for(3 * n, [&](size_t a, size_t b) {
+    if (pos_xyz) for (size_t i = a; i < b; i++) pos_xyz[i] = (double)st[i];
+    if (vel_xyz) for (size_t i = a; i < b; i++) vel_xyz[i] = (double)st[3 * n + i];
+  });
+  if (density) parallel_for(n, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) density[i] = (double)st[6 * n + i]; });
+  return PBF_OK;
+}
+
+extern "C" {
+
+int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz) {
+  if (!h || (n && (!pos_xyz || !vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload: null argument");
+  if (n > 0xFFFFFFF0ull) return fail(h, PBF_ERR_INVALID, "pbf_upload: more than 2^32 particles");
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
+  CK(h, cudaSetDevice(h->device));
+  int rc = ensure_capacity(h, n);
+  if (rc != PBF_OK) return rc;
+  h->n = n; h->cur = 0; h->have_neighbors = false;
+  h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
+  return io_upload(h, n, pos_xyz, vel_xyz);
 }
 
 int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz) {
@@ -354,34 +396,9 @@ int pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, float
 
 int pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density) {
   if (!h) return PBF_ERR_INVALID;
-  const size_t n = h->n;
-  if (n == 0) return pbf_sync(h);
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_download");
   CK(h, cudaSetDevice(h->device));
-  HandleExtra* x = extra_of(h);
-  if ((!pos_xyz || x->registered(pos_xyz, 3 * n * sizeof(double))) && (!vel_xyz || x->registered(vel_xyz, 3 * n * sizeof(double))) &&
-      (!density || x->registered(density, n * sizeof(double)))) {
-    // page-locked caller buffers: scatter to original order as fp64 on the device, DMA straight out
-    CK(h, x->ensure_stage64(7 * h->cap));
-    double* d64 = x->stage64;
-    if (pos_xyz) { enqueue_export3_f64(h, h->pos[h->cur], d64); CK(h, cudaMemcpyAsync(pos_xyz, d64, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
-    if (vel_xyz) { enqueue_export3_f64(h, h->vel[h->cur], d64 + 3 * n); CK(h, cudaMemcpyAsync(vel_xyz, d64 + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
-    if (density) { enqueue_export1_f64(h, h->rho, d64 + 6 * n); CK(h, cudaMemcpyAsync(density, d64 + 6 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); }
-    return pbf_sync(h);
-  }
-  CK(h, x->pin.ensure(7 * n));
-  float* st = x->pin.p;
-  float* d = h->io_stage;
-  if (pos_xyz) { enqueue_export3(h, h->pos[h->cur], d); CK(h, cudaMemcpyAsync(st, d, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
-  if (vel_xyz) { enqueue_export3(h, h->vel[h->cur], d + 3 * n); CK(h, cudaMemcpyAsync(st + 3 * n, d + 3 * n, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
-  if (density) { enqueue_export1(h, h->rho, d + 6 * n); CK(h, cudaMemcpyAsync(st + 6 * n, d + 6 * n, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream)); }
-  int rc = pbf_sync(h);
-  if (rc != PBF_OK) return rc;
-  parallel_for(3 * n, [&](size_t a, size_t b) {
-    if (pos_xyz) for (size_t i = a; i < b; i++) pos_xyz[i] = (double)st[i];
-    if (vel_xyz) for (size_t i = a; i < b; i++) vel_xyz[i] = (double)st[3 * n + i];
-  });
-  if (density) parallel_for(n, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) density[i] = (double)st[6 * n + i]; });
-  return PBF_OK;
+  return io_download(h, pos_xyz, vel_xyz, density);
 }
 
 // Page-lock caller-owned host buffers (cudaHostRegister) so that pbf_upload / pbf_download can DMA

@@ -107,6 +107,8 @@ void enqueue_confine(Solver* h);
 int  alloc_particle_arrays(Solver* h, size_t cap);          // pbf_api.cu
 int  fill_dev_params(const PbfParams& p, DevParams& d, std::string& err);
 int  sync_and_check(Solver* h);
+int  io_upload(Solver* h, size_t n, const double* pos_xyz, const double* vel_xyz);     // pbf_api.cu
+int  io_download(Solver* h, double* pos_xyz, double* vel_xyz, double* density);
 void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz);
 void enqueue_export3(Solver* h, const float4* src, float* dst_xyz);
 void enqueue_export1(Solver* h, const float* src, float* dst);

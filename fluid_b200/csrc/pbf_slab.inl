@@ -195,26 +195,9 @@ int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double
   h->n = n; h->cur = 0; h->have_neighbors = false;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   if (n == 0) return PBF_OK;
-  std::vector<float> st(6 * n);
-  {
-    const unsigned nt = n < (1u << 16) ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    std::vector<std::thread> th;
-    const size_t chunk = (3 * n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; t++) {
-      const size_t a = t * chunk, b = std::min(3 * n, a + chunk);
-      if (a < b) th.emplace_back([&, a, b] { for (size_t i = a; i < b; i++) { st[i] = (float)pos_xyz[i]; st[3 * n + i] = (float)vel_xyz[i]; } });
-    }
-    for (auto& t : th) t.join();
-  }
-  uint32_t* d_ids = nullptr;
-  SCK(h, cudaMalloc((void**)&d_ids, n * 4));
-  SCK(h, cudaMemcpyAsync(h->io_stage, st.data(), 6 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  SCK(h, cudaMemcpyAsync(d_ids, ids, n * 4, cudaMemcpyHostToDevice, h->stream));
-  k_import_ids<<<blocks_for(n), TPB, 0, h->stream>>>((uint32_t)n, h->io_stage, h->io_stage + 3 * n, d_ids, h->pos[0], h->vel[0], h->orig[0]);
-  h->launches++;
-  SCK(h, cudaStreamSynchronize(h->stream));
-  cudaFree(d_ids);
-  SCK(h, cudaGetLastError());
+  int rc = io_upload(h, n, pos_xyz, vel_xyz);            // sets orig = identity ...
+  if (rc != PBF_OK) return rc;
+  SCK(h, cudaMemcpy(h->orig[0], ids, n * 4, cudaMemcpyHostToDevice));   // ... replaced by the global ids
   return PBF_OK;
 }
 
@@ -322,19 +305,9 @@ int pbf_slab_download(pbf_handle* h, size_t cap, double* pos_xyz, double* vel_xy
   const size_t n = h->r_cnt;
   if (n_out) *n_out = n;
   if (n > cap) return sfail(h, PBF_ERR_CAPACITY, "pbf_slab_download: output buffers too small");
-  if (n == 0) return sync_and_check(h);
-  float* d = h->io_stage;
-  enqueue_export3(h, h->pos[h->cur], d);
-  enqueue_export3(h, h->vel[h->cur], d + 3 * n);
-  enqueue_export1(h, h->rho, d + 6 * n);      // rho is indexed by sorted position; exported range-relative below
-  int rc = sync_and_check(h);
+  int rc = io_download(h, pos_xyz, vel_xyz, density);    // range order (orig == nullptr in slab mode)
   if (rc != PBF_OK) return rc;
-  std::vector<float> st(7 * n);
-  SCK(h, cudaMemcpy(st.data(), d, 7 * n * sizeof(float), cudaMemcpyDeviceToHost));
-  if (pos_xyz) for (size_t i = 0; i < 3 * n; i++) pos_xyz[i] = (double)st[i];
-  if (vel_xyz) for (size_t i = 0; i < 3 * n; i++) vel_xyz[i] = (double)st[3 * n + i];
-  if (density) for (size_t i = 0; i < n; i++) density[i] = (double)st[6 * n + i];
-  if (ids) SCK(h, cudaMemcpy(ids, h->orig[h->cur] + h->r_i0, n * 4, cudaMemcpyDeviceToHost));
+  if (ids && n) SCK(h, cudaMemcpy(ids, h->orig[h->cur] + h->r_i0, n * 4, cudaMemcpyDeviceToHost));
   return PBF_OK;
 }
 

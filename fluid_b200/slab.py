@@ -260,6 +260,18 @@ class SlabSolver:
     def local_ids(self):
         return self._ids
 
+    def pin(self, *arrays):
+        """Page-lock caller arrays reused for upload_local / download_local_into (pbf_host_register)."""
+        self.solver.pin(*arrays)
+
+    def download_local_into(self, P, V, R, I):
+        """Owned particles into caller-provided (ideally pinned) arrays of capacity >= n_owned; returns n."""
+        self.sync()
+        n = C.c_size_t()
+        self._ck(self.lib.pbf_slab_download(self.h, P.shape[0], P.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p),
+                                            R.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value
+
     def neighbor_digest(self):
         self.sync()
         cap = max(self.n_owned(), 1)
