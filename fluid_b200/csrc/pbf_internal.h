@@ -23,10 +23,10 @@ struct Scalars {
 };
 
 enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
-                K_VELOCITY, K_VORT_XSPH, K_CONFINE, K_DENSITY, K_IO, K_SLAB, K_COUNT };
+                K_VELOCITY, K_VORT_XSPH, K_CONFINE, K_DENSITY, K_IO, K_SLAB, K_SOLVE_FUSED, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
   "predict_collide_hash", "cell_scan", "scatter", "cell_sort", "reorder", "build_neighbors", "lambda",
-  "delta_collide", "velocity", "vorticity_xsph", "confine_commit", "density_only", "io", "slab"};
+  "delta_collide", "velocity", "vorticity_xsph", "confine_commit", "density_only", "io", "slab", "solve_fused"};
 
 struct Solver {
   int device = 0;
@@ -61,6 +61,8 @@ struct Solver {
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
   int capture_xpred = 0;
+  int fused_state = 0;               // 0 unknown, 1 cooperative fused iterations available, -1 not
+  unsigned fused_grid = 0;
   bool have_neighbors = false;
 
   uint64_t launches = 0, steps_done = 0;
@@ -99,6 +101,7 @@ void enqueue_estimate_densities(Solver* h);
 void enqueue_predict_hash(Solver* h, int apply_forces);
 void enqueue_sort(Solver* h, size_t n_in);
 void enqueue_build(Solver* h, int include_self);
+bool enqueue_solve_fused(Solver* h);
 void enqueue_lambda(Solver* h, int first_iter);
 void enqueue_delta(Solver* h);
 void enqueue_velocity(Solver* h);
