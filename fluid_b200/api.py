@@ -63,6 +63,7 @@ def load_library():
         "pbf_sync": (i32, [vp]),
         "pbf_estimate_densities": (i32, [vp]),
         "pbf_stats": (i32, [vp, vp, vp, vp]),
+        "pbf_density_at": (i32, [vp, sz, vp, vp]),
         "pbf_upload_device": (i32, [vp, sz, vp, vp]),
         "pbf_download_device": (i32, [vp, vp, vp, vp]),
         "pbf_debug_neighbor_digest": (i32, [vp, vp, vp]),
@@ -165,6 +166,13 @@ class Solver:
 
     def download_into(self, P, V, R):
         self._ck(self.lib.pbf_download(self.h, _ptr(P), _ptr(V), _ptr(R)))
+
+    def density_at(self, query):
+        """Particles::estimateDensityAt for an [m,3] array of points."""
+        q = np.ascontiguousarray(query, dtype=np.float64)
+        out = np.empty(q.shape[0])
+        self._ck(self.lib.pbf_density_at(self.h, q.shape[0], _ptr(q), _ptr(out)))
+        return out
 
     def stats(self):
         a, b, ms = C.c_double(), C.c_double(), C.c_double()

@@ -327,7 +327,7 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   CK(h, cudaSetDevice(h->device));
   int rc = ensure_capacity(h, n);
   if (rc != PBF_OK) return rc;
-  h->n = n; h->cur = 0; h->have_neighbors = false;
+  h->n = n; h->cur = 0; h->have_neighbors = false; h->rebinned_at = -1;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   return io_upload(h, n, pos_xyz, vel_xyz);
 }
@@ -399,6 +399,42 @@ int pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* densit
   if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_download");
   CK(h, cudaSetDevice(h->device));
   return io_download(h, pos_xyz, vel_xyz, density);
+}
+
+// Particles::estimateDensityAt (particles.cpp:446-453) for m query points at once
+int pbf_density_at(pbf_handle* h, size_t m, const double* query_xyz, double* density_out) {
+  if (!h || (m && (!query_xyz || !density_out))) return PBF_ERR_INVALID;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "pbf_density_at is single-GPU only");
+  if (m > 0x7FFFFFFFull) return fail(h, PBF_ERR_INVALID, "too many query points in one call");
+  if (m == 0) return PBF_OK;
+  CK(h, cudaSetDevice(h->device));
+  if (h->n == 0) { for (size_t i = 0; i < m; i++) density_out[i] = 0.0; return PBF_OK; }
+  if (h->rebinned_at != (long long)h->steps_done) {     // cells of the last step belong to the predicted positions
+    enqueue_rebin(h);
+    h->have_neighbors = false;
+    h->rebinned_at = (long long)h->steps_done;
+  }
+  std::vector<float> q(4 * m);
+  parallel_for(m, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) { q[4*i] = (float)query_xyz[3*i]; q[4*i+1] = (float)query_xyz[3*i+1]; q[4*i+2] = (float)query_xyz[3*i+2]; q[4*i+3] = 0.f; }
+  });
+  float4* dq = nullptr; float* dout = nullptr;
+  CK(h, dmalloc(&dq, m)); CK(h, dmalloc(&dout, m));
+  cudaError_t e = cudaMemcpyAsync(dq, q.data(), m * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    enqueue_density_at(h, (uint32_t)m, dq, dout);
+    std::vector<float> o(m);
+    e = cudaMemcpyAsync(o.data(), dout, m * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    int rc = sync_and_check(h);
+    cudaFree(dq); cudaFree(dout);
+    if (rc != PBF_OK) return rc;
+    if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); return PBF_ERR_CUDA; }
+    for (size_t i = 0; i < m; i++) density_out[i] = (double)o[i];
+    return PBF_OK;
+  }
+  cudaFree(dq); cudaFree(dout);
+  h->last_error = cudaGetErrorString(e);
+  return PBF_ERR_CUDA;
 }
 
 // Page-lock caller-owned host buffers (cudaHostRegister) so that pbf_upload / pbf_download can DMA

@@ -64,6 +64,7 @@ struct Solver {
   int fused_state = 0;               // 0 unknown, 1 cooperative fused iterations available, -1 not
   unsigned fused_grid = 0;
   bool have_neighbors = false;
+  long long rebinned_at = -1;        // steps_done when the arrays were last re-binned by committed position
 
   uint64_t launches = 0, steps_done = 0;
   double last_call_ms = 0.0;
@@ -112,6 +113,8 @@ int  fill_dev_params(const PbfParams& p, DevParams& d, std::string& err);
 int  sync_and_check(Solver* h);
 int  io_upload(Solver* h, size_t n, const double* pos_xyz, const double* vel_xyz);     // pbf_api.cu
 int  io_download(Solver* h, double* pos_xyz, double* vel_xyz, double* density);
+void enqueue_rebin(Solver* h);
+void enqueue_density_at(Solver* h, uint32_t m, const float4* d_q, float* d_out);
 void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz);
 void enqueue_export3(Solver* h, const float4* src, float* dst_xyz);
 void enqueue_export1(Solver* h, const float* src, float* dst);

@@ -573,6 +573,36 @@ k_density_only(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, con
   rho_out[i] = P.poly6_c * w3s;
 }
 
+// SPH density at arbitrary query points: Particles::estimateDensityAt (particles.cpp:446-453), the field
+// the marching-cubes surfacer samples (particles.cpp:350-418).  xs = committed positions sorted by
+// their own cells (the caller re-bins first); the reference's sum over ALL particles equals the sum
+// over the 27-cell neighbourhood because poly6 vanishes beyond h.
+__global__ void __launch_bounds__(TPB)
+k_density_at(const __grid_constant__ DevParams P, uint32_t m, const float4* __restrict__ q, const float4* __restrict__ xs,
+             const uint32_t* __restrict__ cell_start, float* __restrict__ out) {
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  if (t >= m) return;
+  const float4 pi = q[t];
+  const int3 c = cell_coords(P, pi.x, pi.y, pi.z);
+  const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, P.gdim[2] - 1);
+  float w3s = 0.f;
+#pragma unroll 1
+  for (int k = 0; k < 9; k++) {
+    const int cx = c.x + (k / 3) - 1, cy = c.y + (k % 3) - 1;
+    if (cx < 0 || cx >= P.gdim[0] || cy < 0 || cy >= P.gdim[1]) continue;
+    const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
+    const uint32_t jb = cell_start[base + zlo], je = cell_start[base + zhi + 1];
+#pragma unroll 4
+    for (uint32_t j = jb; j < je; j++) {
+      const float4 pj = __ldg(&xs[j]);
+      const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      const float tt = fmaxf(P.h2 - fmaf(dz, dz, fmaf(dy, dy, dx * dx)), 0.f);
+      w3s = fmaf(tt * tt, tt, w3s);
+    }
+  }
+  out[t] = P.poly6_c * w3s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // H. I/O helpers: original order <-> sorted order, fp32 AoS xyz <-> float4 SoA
 // ------------------------------------------------------------------------------------------------
@@ -786,6 +816,19 @@ void enqueue_estimate_densities(Solver* h) {
   enqueue_sort(h, n);
   enqueue_build(h, 1);
   LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, 0u, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt);
+}
+
+// re-bin the particles by their COMMITTED positions (after a step the cells are those of the predicted
+// positions): afterwards xs_a = sorted committed positions and cell_start matches them
+void enqueue_rebin(Solver* h) {
+  const uint32_t n = (uint32_t)h->n;
+  if (n == 0) return;
+  h->r_i0 = 0; h->r_cnt = n; h->n_sorted = n;
+  enqueue_predict_hash(h, 0);
+  enqueue_sort(h, n);
+}
+void enqueue_density_at(Solver* h, uint32_t m, const float4* d_q, float* d_out) {
+  LAUNCH(h, K_DENSITY, k_density_at, blocks_for(m), h->dp, m, d_q, h->xs_a, h->cell_start, d_out);
 }
 
 void enqueue_import(Solver* h, const float* d_pos_xyz, const float* d_vel_xyz) {

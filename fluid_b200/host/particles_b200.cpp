@@ -102,6 +102,14 @@ double Particles::estimateDensityAt(Vector3D pos) const {
   return density;
 }
 
+std::vector<double> Particles::estimateDensitiesAt(const std::vector<Vector3D>& points) {
+  ensureUploaded();
+  std::vector<double> q(3 * points.size()), out(points.size());
+  for (size_t i = 0; i < points.size(); i++) { q[3*i] = points[i].x; q[3*i+1] = points[i].y; q[3*i+2] = points[i].z; }
+  if (pbf_density_at(handle_, points.size(), q.data(), out.data()) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  return out;
+}
+
 std::string Particles::paramsString() const {
   std::stringstream ss;
   ss << "Fluid simulation parameters: " << std::endl

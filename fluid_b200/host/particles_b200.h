@@ -59,7 +59,9 @@ struct Particles {
   void timeStep(double delta_t);                 // particles.cpp:250-297 (delta_t must equal params.dt)
   void timeStep();                               // particles.cpp:299-301
   void estimateDensities();                      // particles.cpp:440-444
-  double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host; marching-cubes consumer)
+  double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
+  // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
+  std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);
   std::string paramsString() const;              // particles.cpp:420-438
   // the two numbers of the reference's "avg rho: a => b" line for the last step
   double avg_rho_first_iter = 0.0, avg_rho_final = 0.0;

@@ -92,6 +92,11 @@ int  pbf_estimate_densities(pbf_handle* h);     /* load-time density incl. self 
  * (the two numbers the reference prints), and the device time of the last pbf_step call. */
 int  pbf_stats(pbf_handle* h, double* avg_rho_first_iter, double* avg_rho_final, double* last_call_ms);
 
+/* SPH density at m arbitrary points from the committed positions = Particles::estimateDensityAt
+ * (particles.cpp:446-453), the scalar field the marching-cubes surfacer samples
+ * (particles.cpp:350-418).  Host fp64 AoS in, fp64 out; single GPU. */
+int  pbf_density_at(pbf_handle* h, size_t m, const double* query_xyz, double* density_out);
+
 /* ---- device-resident I/O (bench "value" leg; fp32 xyz AoS device pointers, original order) */
 int  pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz);
 int  pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, float* d_density);

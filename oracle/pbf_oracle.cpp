@@ -2,6 +2,8 @@
 // Built by oracle/Makefile into oracle/liboracle.so.  Never linked into the product library.
 #include "pbf_oracle.hpp"
 
+#include <type_traits>
+
 #include <chrono>
 #include <omp.h>
 
@@ -83,6 +85,18 @@ void oracle_download_array(void* hv, int which, double* out) {
         case PBF_ARRAY_XPRED: out[3*i] = o.xpred[i].x; out[3*i+1] = o.xpred[i].y; out[3*i+2] = o.xpred[i].z; break;
       }
     }
+    return 0;
+  });
+}
+
+// Particles::estimateDensityAt (particles.cpp:446-453) at m query points
+void oracle_density_at(void* hv, size_t m, const double* q, double* out) {
+  visit((Handle*)hv, [&](auto& o) {
+    typedef typename std::remove_reference<decltype(o)>::type O;
+    typedef typename O::V V;
+    #pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)m; i++)
+      out[i] = (double)o.density_at(V((decltype(o.H))q[3*i], (decltype(o.H))q[3*i+1], (decltype(o.H))q[3*i+2]));
     return 0;
   });
 }

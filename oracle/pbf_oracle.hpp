@@ -260,6 +260,13 @@ struct Oracle {
     }
   }
 
+  // particles.cpp:446-453 estimateDensityAt: sum of poly6(x_p - q) over ALL particles, index order
+  R density_at(const V& q) const {
+    R d = R(0);
+    for (size_t i = 0; i < n; i++) d += poly6(pos[i] - q);
+    return d;
+  }
+
   // particles.cpp:258-265: inclusive predicate on predicted positions, ascending index lists,
   // self excluded (the reference's i<j double loop).  Grid search = conservative binning + the
   // same predicate + ascending sort, so both searches give identical lists.

@@ -9,6 +9,9 @@
 //   * calls Particles::timeStep() (particles.cpp:250-301) and dumps state after each step.
 //
 // Usage: ref_harness (--xml file.xml | --bin file.bin) --steps S --out dump.bin [--quiet]
+//                    [--density-queries q.bin --density-out d.bin]
+//   q.bin : int64 M, M*3 doubles; d.bin : M doubles = Particles::estimateDensityAt(q) after the last
+//           step (particles.cpp:446-453, the field marching cubes samples).
 //   .bin input : int64 N, double rho0 (already rounded through float like stof, Q17),
 //                N*3 doubles pos, N*3 doubles vel.
 //   dump       : "PBFDUMP1", int64 N, int64 S, then per step:
@@ -84,7 +87,7 @@ static void add_quad(std::vector<Primitive*>& prims, Vector3D a, Vector3D b, Vec
 }
 
 int main(int argc, char** argv) {
-  const char *xml = nullptr, *bin = nullptr, *out = nullptr;
+  const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr;
   int steps = 1; bool quiet = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -93,6 +96,8 @@ int main(int argc, char** argv) {
     else if (a == "--out" && i + 1 < argc) out = argv[++i];
     else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
     else if (a == "--quiet") quiet = true;
+    else if (a == "--density-queries" && i + 1 < argc) dq = argv[++i];
+    else if (a == "--density-out" && i + 1 < argc) dout = argv[++i];
     else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
   }
   if ((!xml && !bin)) { fprintf(stderr, "need --xml or --bin\n"); return 2; }
@@ -155,6 +160,18 @@ int main(int argc, char** argv) {
     fwrite(&dt, 8, 1, f);
   }
   if (f) fclose(f);
+  if (dq && dout) {
+    FILE* q = fopen(dq, "rb");
+    int64_t m = 0;
+    if (!q || fread(&m, 8, 1, q) != 1) { fprintf(stderr, "cannot read %s\n", dq); return 1; }
+    std::vector<double> pts(3 * m), dens(m);
+    if (fread(pts.data(), 8, 3 * m, q) != (size_t)(3 * m)) { fprintf(stderr, "short read %s\n", dq); return 1; }
+    fclose(q);
+    for (int64_t i = 0; i < m; i++) dens[i] = ps->estimateDensityAt(Vector3D(pts[3*i], pts[3*i+1], pts[3*i+2]));
+    FILE* o = fopen(dout, "wb");
+    fwrite(dens.data(), 8, m, o);
+    fclose(o);
+  }
 
   std::cout.rdbuf(old_out);
   std::cerr.rdbuf(old_err);

@@ -38,6 +38,25 @@ def run_reference(pos, vel, rho0, steps):
         return read_dump(dump), log
 
 
+def density_queries():
+    """Marching-cubes style lattice over the Cornell box at step H/2 (FSTEPSIZE_RATIO 0.5,
+    particles.cpp:18) plus random points, some outside the box."""
+    g = np.stack(np.meshgrid(np.arange(-1.05, 1.06, 0.15), np.arange(-0.05, 1.56, 0.15), np.arange(-1.05, 1.06, 0.15), indexing="ij"), -1).reshape(-1, 3)
+    r = np.random.default_rng(77).uniform([-1.3, -0.3, -1.3], [1.3, 1.8, 1.3], size=(500, 3))
+    return np.concatenate([g, r])
+
+
+def reference_density_field(pos, vel, rho0, q):
+    """Particles::estimateDensityAt (particles.cpp:446-453) of the unmodified reference on the loaded scene."""
+    with tempfile.TemporaryDirectory() as td:
+        scene = os.path.join(td, "scene.bin"); qf = os.path.join(td, "q.bin"); df = os.path.join(td, "d.bin")
+        write_bin_scene(scene, pos, vel, rho0)
+        with open(qf, "wb") as f:
+            f.write(np.int64(q.shape[0]).tobytes()); f.write(np.ascontiguousarray(q, dtype=np.float64).tobytes())
+        subprocess.run([ref_harness_path(), "--bin", scene, "--steps", "0", "--density-queries", qf, "--density-out", df, "--quiet"], check=True)
+        return np.fromfile(df, dtype=np.float64)
+
+
 def pack(dump, log, keep):
     lines = re.findall(r"avg rho: (\S+) => (\S+)", log)
     out = dict(
@@ -85,6 +104,12 @@ def main():
         dump, log = run_reference(pos, vel, rho0, 6)
         np.savez_compressed(os.path.join(GOLDEN, f"ref_jitter_{name}.npz"), pos=pos, vel=vel, rho0=rho0, **pack(dump, log, (0, 1, 5)))
         print("jitter", name, pos.shape[0], "pairs", [len(d["col"]) for d in dump])
+    # density field (marching-cubes input) of two loaded scenes
+    q = density_queries()
+    for name, (pos, vel, rho0) in list(jitter_scenes().items())[:2]:
+        d = reference_density_field(pos, vel, rho0, q)
+        np.savez_compressed(os.path.join(GOLDEN, f"ref_density_{name}.npz"), pos=pos, vel=vel, rho0=rho0, q=q, density=d)
+        print("density field", name, q.shape[0], "points, max", d.max())
 
 
 if __name__ == "__main__":

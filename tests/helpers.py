@@ -61,6 +61,7 @@ def oracle_lib():
         lib.oracle_step.argtypes = [C.c_void_p, C.c_int]
         lib.oracle_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_download_array.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.oracle_density_at.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         lib.oracle_num_pairs.restype = C.c_size_t
         lib.oracle_num_pairs.argtypes = [C.c_void_p]
         lib.oracle_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -127,6 +128,11 @@ class Oracle:
     def array(self, which):
         out = np.empty(self.n if which == ARRAY_LAMBDA else (self.n, 3))
         self.lib.oracle_download_array(self.h, which, _ptr(out))
+        return out
+
+    def density_at(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64); out = np.empty(q.shape[0])
+        self.lib.oracle_density_at(self.h, q.shape[0], _ptr(q), _ptr(out))
         return out
 
     def neighbors(self):

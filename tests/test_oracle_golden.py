@@ -130,3 +130,12 @@ def test_oracle_matches_live_reference(tmp_path):
         assert np.array_equal(P, d[s]["state"][:, 0:3]) and np.array_equal(V, d[s]["state"][:, 3:6])
         assert np.array_equal(R, d[s]["state"][:, 6])
         assert np.array_equal(o.neighbors()[1].astype(np.int32), d[s]["col"])
+
+
+@pytest.mark.parametrize("name", ["two_blocks", "sparse"])
+def test_density_field_matches_reference(name):
+    """Particles::estimateDensityAt (particles.cpp:446-453), the marching-cubes field: bit-exact."""
+    ref = np.load(os.path.join(GOLDEN, f"ref_density_{name}.npz"))
+    o = Oracle(default_params(rest_density=float(ref["rho0"])), 64, COLLIDE_TRIANGLES, SEARCH_GRID)
+    o.upload(ref["pos"], ref["vel"])
+    assert np.array_equal(o.density_at(ref["q"]), ref["density"])
