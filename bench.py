@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=ITERATIONS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tank", action="store_true", help="N=1 only: run the per-GPU wide-tank slab workload instead of C4 (weak-scaling reference point)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -209,7 +210,7 @@ def main():
     iters = args.iterations
     hbm_peak, peak_src = measured_peaks()
 
-    if world == 1:
+    if world == 1 and not args.tank:
         box_max = (max(120.0, 0.3 * nx), 30.0, SPACING * nz + 0.1)
         params = api.default_params(rest_density=RHO0, iterations=iters, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
         solver = api.Solver(params, device=local_rank)
@@ -239,7 +240,8 @@ def main():
 
     # warm-up
     step_fn(args.warmup); sync_fn(); barrier()
-    base = solver.solver if world > 1 else solver
+    slab_mode = world > 1 or args.tank
+    base = solver.solver if slab_mode else solver
     base.profile_enable(True)
     launches0 = base.launch_count()
     sampler = ClockSampler(local_rank); sampler.start()
@@ -248,7 +250,7 @@ def main():
     step_fn(args.steps); sync_fn()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    dev_ms = solver.last_ms() if world > 1 else solver.stats()[2]      # CUDA events on the solver's stream
+    dev_ms = solver.last_ms() if slab_mode else solver.stats()[2]      # CUDA events on the solver's stream
     barrier()
     clocks = sampler.stop()
     launches = base.launch_count() - launches0
@@ -290,7 +292,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         k2 = max(2, min(args.steps, 5))
-        if world == 1:
+        if not slab_mode:
             P = np.empty((n_local, 3)); V = np.empty((n_local, 3)); R = np.empty(n_local)
             solver.pin(P, V, R)          # the host arrays a caller reuses every step, page-locked once (pbf_host_register)
             solver.download_into(P, V, R)
@@ -317,7 +319,7 @@ def main():
                        "(page-locked caller buffers, fp64 on the wire, fp64<->fp32 on the device); wall clock"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.tank:
         cpu = cpu_baseline_port()
 
     if rank == 0:

@@ -103,10 +103,11 @@ void enqueue_predict_hash(Solver* h, int apply_forces);
 void enqueue_sort(Solver* h, size_t n_in);
 void enqueue_build(Solver* h, int include_self);
 bool enqueue_solve_fused(Solver* h);
-void enqueue_lambda(Solver* h, int first_iter);
-void enqueue_delta(Solver* h);
+enum { PART_ALL = 0, PART_BOUNDARY = 1, PART_INTERIOR = 2 };
+void enqueue_lambda(Solver* h, int first_iter, int part);
+void enqueue_delta(Solver* h, int part);
 void enqueue_velocity(Solver* h);
-void enqueue_vorticity(Solver* h);
+void enqueue_vorticity(Solver* h, int part);
 void enqueue_confine(Solver* h);
 int  alloc_particle_arrays(Solver* h, size_t cap);          // pbf_api.cu
 int  fill_dev_params(const PbfParams& p, DevParams& d, std::string& err);

@@ -383,10 +383,11 @@ __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t,
 }
 
 __global__ void __launch_bounds__(TPB)
-k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs_in,
+k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multiple of 32 */, uint32_t n /* end of the t range */,
+         const float4* __restrict__ xs_in,
          float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
          const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
-  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
   float rho = 0.f;
   if (t < n) rho = lambda_particle<true>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out);
   if (rho_sum) block_sum_to_double(rho, rho_sum);
@@ -426,10 +427,10 @@ __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, u
 
 template <int NCORR>
 __global__ void __launch_bounds__(TPB)
-k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs_in,
+k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
         const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
   if (t >= n) return;
   delta_particle<NCORR, true>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt);
 }
@@ -472,12 +473,12 @@ k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __rest
 }
 
 __global__ void __launch_bounds__(TPB)
-k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
+k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs,
                  float4* __restrict__ xs_w, const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
                  double* __restrict__ rho_sum) {
-  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   float rho = 0.f;
   if (t < n) {
@@ -734,21 +735,47 @@ void enqueue_build(Solver* h, int include_self) {
          h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
 }
 
-void enqueue_lambda(Solver* h, int first_iter) {
-  LAUNCH(h, K_LAMBDA, k_lambda, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->xs_b, h->nbr, h->slice_off, h->nbr_cnt,
-         (float*)nullptr, first_iter ? &h->sc->rho_first : (double*)nullptr);
+// Sub-ranges of the owned range for overlapping halo exchange with compute (slab mode):
+// PART_BOUNDARY = the first / last owned cell column rounded outwards to whole slices (what the
+// x-neighbours need as ghosts), PART_INTERIOR = the rest, PART_ALL = everything.
+static int part_ranges(const Solver* h, int part, uint32_t rng[2][2]) {
+  const uint32_t cnt = h->r_cnt;
+  if (part == PART_ALL || !h->slab) { rng[0][0] = 0; rng[0][1] = cnt; return part == PART_INTERIOR ? 0 : 1; }
+  const uint32_t nl = h->has_left ? h->bounds[1] - h->bounds[0] : 0u, nr = h->has_right ? h->bounds[3] - h->bounds[2] : 0u;
+  uint32_t l_end = std::min(cnt, (nl + 31u) & ~31u), r_begin = (cnt - std::min(cnt, nr)) & ~31u;
+  if (r_begin < l_end) r_begin = l_end;                   // thin slab: the two boundary parts meet
+  if (part == PART_INTERIOR) { rng[0][0] = l_end; rng[0][1] = r_begin; return r_begin > l_end ? 1 : 0; }
+  int k = 0;
+  if (l_end > 0) { rng[k][0] = 0; rng[k][1] = l_end; k++; }
+  if (cnt > r_begin) { rng[k][0] = r_begin; rng[k][1] = cnt; k++; }
+  return k;
 }
-void enqueue_delta(Solver* h) {
-  const unsigned g = blocks_for(h->r_cnt);
-  if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, h->r_i0, h->r_cnt, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
-  else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, h->r_i0, h->r_cnt, h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+
+void enqueue_lambda(Solver* h, int first_iter, int part) {
+  uint32_t rng[2][2];
+  const int k = part_ranges(h, part, rng);
+  for (int q = 0; q < k; q++)
+    LAUNCH(h, K_LAMBDA, k_lambda, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_b, h->nbr,
+           h->slice_off, h->nbr_cnt, (float*)nullptr, first_iter ? &h->sc->rho_first : (double*)nullptr);
+}
+void enqueue_delta(Solver* h, int part) {
+  uint32_t rng[2][2];
+  const int k = part_ranges(h, part, rng);
+  for (int q = 0; q < k; q++) {
+    const unsigned g = blocks_for(rng[q][1] - rng[q][0]);
+    if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+    else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+  }
 }
 void enqueue_velocity(Solver* h) {   // every sorted particle, ghosts included (their x and x* are bit-identical to the owner's)
   LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp);
 }
-void enqueue_vorticity(Solver* h) {
-  LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_a, h->xs_tmp, h->vtmp, h->vel[h->cur], h->omega,
-         h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
+void enqueue_vorticity(Solver* h, int part) {
+  uint32_t rng[2][2];
+  const int k = part_ranges(h, part, rng);
+  for (int q = 0; q < k; q++)
+    LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_tmp, h->vtmp,
+           h->vel[h->cur], h->omega, h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
 }
 void enqueue_confine(Solver* h) {
   LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
@@ -801,9 +828,9 @@ void enqueue_step(Solver* h) {
   enqueue_build(h, 0);
   if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
   if (!enqueue_solve_fused(h))
-    for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0); enqueue_delta(h); }
+    for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
   enqueue_velocity(h);
-  enqueue_vorticity(h);
+  enqueue_vorticity(h, PART_ALL);
   enqueue_confine(h);
   h->steps_done++;
 }

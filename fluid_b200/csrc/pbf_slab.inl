@@ -271,15 +271,17 @@ int pbf_slab_phase_sort(pbf_handle* h, uint32_t bounds_out[5]) {
   return PBF_OK;
 }
 
-int pbf_slab_phase(pbf_handle* h, int phase) {
-  if (!h || !h->slab) return PBF_ERR_INVALID;
+int pbf_slab_phase(pbf_handle* h, int phase) { return pbf_slab_phase_part(h, phase, PBF_PART_ALL); }
+
+int pbf_slab_phase_part(pbf_handle* h, int phase, int part) {
+  if (!h || !h->slab || part < PBF_PART_ALL || part > PBF_PART_INTERIOR) return PBF_ERR_INVALID;
   SCK(h, cudaSetDevice(h->device));
   switch (phase) {
-    case PBF_PHASE_LAMBDA_FIRST: enqueue_lambda(h, 1); break;
-    case PBF_PHASE_LAMBDA: enqueue_lambda(h, 0); break;
-    case PBF_PHASE_DELTA: enqueue_delta(h); break;
+    case PBF_PHASE_LAMBDA_FIRST: enqueue_lambda(h, 1, part); break;
+    case PBF_PHASE_LAMBDA: enqueue_lambda(h, 0, part); break;
+    case PBF_PHASE_DELTA: enqueue_delta(h, part); break;
     case PBF_PHASE_VELOCITY: enqueue_velocity(h); break;
-    case PBF_PHASE_VORTICITY: enqueue_vorticity(h); break;
+    case PBF_PHASE_VORTICITY: enqueue_vorticity(h, part); break;
     case PBF_PHASE_CONFINE: enqueue_confine(h); h->steps_done++; break;
     default: return sfail(h, PBF_ERR_INVALID, "unknown phase");
   }

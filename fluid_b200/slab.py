@@ -20,6 +20,7 @@ from . import api
 (BUF_MIG_SEND_L, BUF_MIG_SEND_R, BUF_MIG_RECV_L, BUF_MIG_RECV_R, BUF_GHOST_SEND_L, BUF_GHOST_SEND_R,
  BUF_GHOST_RECV_L, BUF_GHOST_RECV_R, BUF_XS_A, BUF_XS_B, BUF_OMEGA, BUF_XS_W) = range(12)
 PH_LAMBDA_FIRST, PH_LAMBDA, PH_DELTA, PH_VELOCITY, PH_VORTICITY, PH_CONFINE = range(6)
+PART_ALL, PART_BOUNDARY, PART_INTERIOR = range(3)
 
 
 def _bind(lib):
@@ -38,6 +39,7 @@ def _bind(lib):
         "pbf_slab_phase_migrate": (i32, [vp]),
         "pbf_slab_phase_sort": (i32, [vp, C.POINTER(C.c_uint32 * 5)]),
         "pbf_slab_phase": (i32, [vp, i32]),
+        "pbf_slab_phase_part": (i32, [vp, i32, i32]),
         "pbf_slab_stats": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
         "pbf_slab_buffer": (vp, [vp, i32, C.POINTER(sz)]),
     }
@@ -116,7 +118,7 @@ class _DevMem:
 class SlabSolver:
     """One rank of the slab-decomposed solver."""
 
-    def __init__(self, params, rank, world, device=0, halo_factor=4.0, staged=None):
+    def __init__(self, params, rank, world, device=0, halo_factor=4.0, staged=None, overlap=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -138,6 +140,13 @@ class SlabSolver:
         self.iterations = params.iterations
         # gloo cannot move device memory: stage through the host (tests; ranks sharing one GPU)
         self.staged = (world > 1 and dist.get_backend() != "nccl") if staged is None else staged
+        # Optional (PBF_SLAB_OVERLAP=1): overlap each pass's halo exchange with the interior part of the
+        # same pass on a second stream.  Measured at 2 x 16M particles: 88.1 ms/step overlapped vs
+        # 87.5 ms sequential — the exchanges (~2 MB, NVLink) are not what the step waits for — so off by default.
+        import os
+        want = os.environ.get("PBF_SLAB_OVERLAP", "0") == "1" if overlap is None else overlap
+        self.overlap = bool(want) and world > 1 and not self.staged
+        self.comm_stream = torch.cuda.Stream(device=device) if self.overlap else None
 
     def _ck(self, rc):
         if rc != api.PBF_OK:
@@ -213,15 +222,36 @@ class SlabSolver:
         out = (C.c_uint32 * 5)()
         self._ck(lib.pbf_slab_phase_sort(h, C.byref(out)))
         self.bounds = tuple(int(v) for v in out)
+        if not self.overlap:
+            for it in range(self.iterations):
+                self._ck(lib.pbf_slab_phase(h, PH_LAMBDA_FIRST if it == 0 else PH_LAMBDA))
+                self._halo(BUF_XS_B)
+                self._ck(lib.pbf_slab_phase(h, PH_DELTA))
+                self._halo(BUF_XS_A)
+            self._ck(lib.pbf_slab_phase(h, PH_VELOCITY))
+            self._ck(lib.pbf_slab_phase(h, PH_VORTICITY))
+            self._halo(BUF_XS_W)          # ghost (x*, |omega|): the confinement pass gathers one float4 per pair
+            self._ck(lib.pbf_slab_phase(h, PH_CONFINE))
+            return
+        # overlapped: boundary columns first, their exchange runs on the comm stream while the
+        # interior of the same pass computes; the next pass waits for the exchange
         for it in range(self.iterations):
-            self._ck(lib.pbf_slab_phase(h, PH_LAMBDA_FIRST if it == 0 else PH_LAMBDA))
-            self._halo(BUF_XS_B)
-            self._ck(lib.pbf_slab_phase(h, PH_DELTA))
-            self._halo(BUF_XS_A)
+            self._pass_overlapped(PH_LAMBDA_FIRST if it == 0 else PH_LAMBDA, BUF_XS_B)
+            self._pass_overlapped(PH_DELTA, BUF_XS_A)
         self._ck(lib.pbf_slab_phase(h, PH_VELOCITY))
-        self._ck(lib.pbf_slab_phase(h, PH_VORTICITY))
-        self._halo(BUF_XS_W)          # ghost (x*, |omega|): the confinement pass gathers one float4 per pair
+        self._pass_overlapped(PH_VORTICITY, BUF_XS_W)
         self._ck(lib.pbf_slab_phase(h, PH_CONFINE))
+
+    def _pass_overlapped(self, phase, which):
+        torch = self.torch
+        self._ck(self.lib.pbf_slab_phase_part(self.h, phase, PART_BOUNDARY))
+        ready = torch.cuda.Event(); ready.record(self.stream)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            self._halo(which)
+            done = torch.cuda.Event(); done.record(self.comm_stream)
+        self._ck(self.lib.pbf_slab_phase_part(self.h, phase, PART_INTERIOR))
+        self.stream.wait_event(done)
 
     def step(self, n_steps=1):
         torch = self.torch

@@ -60,6 +60,12 @@ int pbf_slab_phase_sort(pbf_handle* h, uint32_t bounds_out[5]);   /* b0, b1, b2,
 enum { PBF_PHASE_LAMBDA_FIRST = 0, PBF_PHASE_LAMBDA = 1, PBF_PHASE_DELTA = 2, PBF_PHASE_VELOCITY = 3,
        PBF_PHASE_VORTICITY = 4, PBF_PHASE_CONFINE = 5 };
 int pbf_slab_phase(pbf_handle* h, int phase);
+/* Same, restricted to a part of the owned range, so a driver can overlap the halo exchange of a
+ * pass with the bulk of its compute: BOUNDARY = the first and last owned cell columns (rounded
+ * outwards to whole 32-particle slices) = exactly what the x-neighbours receive as ghosts;
+ * INTERIOR = the rest.  LAMBDA*, DELTA and VORTICITY honour `part`; the other phases ignore it. */
+enum { PBF_PART_ALL = 0, PBF_PART_BOUNDARY = 1, PBF_PART_INTERIOR = 2 };
+int pbf_slab_phase_part(pbf_handle* h, int phase, int part);
 /* sums over the owned particles of the last step: density after the first lambda pass / final, count */
 int pbf_slab_stats(pbf_handle* h, double* rho_first_sum, double* rho_final_sum, uint64_t* n_owned);
 

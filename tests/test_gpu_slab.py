@@ -13,13 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
 
 
-def _run(world, extra, port):
+def _run(world, extra, port, env=None):
     if world == 1:
         cmd = [sys.executable, WORKER] + extra
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), WORKER] + extra
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     lines = [l for l in r.stdout.splitlines() if l.startswith("SLAB_RESULT ")]
     assert r.returncode == 0 and lines, f"worker failed:\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
     return json.loads(lines[-1][len("SLAB_RESULT "):])
@@ -55,6 +55,12 @@ def test_three_slabs_shared_gpu_gloo():
 @pytest.mark.skipif("_ngpu() < 2")
 def test_two_slabs_nccl():
     _check(_run(2, ["--backend", "nccl", "--steps", "6"], 29613))
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+def test_two_slabs_nccl_overlapped_exchange():
+    """Boundary columns first, exchange on a second stream while the interior computes: same bits."""
+    _check(_run(2, ["--backend", "nccl", "--steps", "6"], 29615, env={"PBF_SLAB_OVERLAP": "1"}))
 
 
 @pytest.mark.skipif("_ngpu() < 4")
