@@ -39,6 +39,9 @@ k_predict_hash(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, con
   const float4 x = pos[i];
   float3 p = xyz(x);
   float4 v = vel[i];
+  // The reference's hard clamp (std::min/max, particles.cpp:129-131) silently turns a NaN coordinate into
+  // the box corner; report non-finite state instead of hiding it.
+  if (!(isfinite(x.x) && isfinite(x.y) && isfinite(x.z) && isfinite(v.x) && isfinite(v.y) && isfinite(v.z))) atomicOr(&sc->err, ERRBIT_NONFINITE);
   if (apply_forces) {
     v.y = __fsub_rn(v.y, P.gdt);                                   // velocity.y -= 10 * delta_t
     const float3 delta = make_float3(__fmul_rn(v.x, P.dt), __fmul_rn(v.y, P.dt), __fmul_rn(v.z, P.dt));

@@ -352,3 +352,38 @@ def test_density_field_vs_reference_and_oracle(name):
     g.step(1)
     for a, b in zip(g.download(), g2.download()):
         assert np.array_equal(a, b)
+
+
+def test_edge_cases_and_parameter_variants():
+    """Empty / single-particle inputs, re-upload with another size, non-default solver parameters
+    (n_corr != 4 takes the generic exponent path; vorticity / XSPH switched off), two handles at once,
+    and a non-finite input reported as PBF_ERR_DOMAIN."""
+    from fluid_b200 import api
+    pos, vel, rho0, _ = _scene("corner")
+    g = _gpu(rho0)
+    g.upload(np.zeros((0, 3)), np.zeros((0, 3))); g.step(2)
+    P, V, R = g.download()
+    assert P.shape == (0, 3) and R.shape == (0,)
+    g.upload(pos[:1], vel[:1]); g.step(1)                      # one particle: no neighbours at all
+    o = _oracle(rho0, 32); o.upload(pos[:1], vel[:1]); o.step(1)
+    assert np.array_equal(g.download()[0], o.download()[0]) and g.download()[2][0] == 0.0
+    g.upload(pos, vel); g.step(1)                              # same handle, bigger upload
+    g2 = _gpu(rho0); g2.upload(pos, vel); g2.step(1)           # second handle alive at the same time
+    for a, b in zip(g.download(), g2.download()):
+        assert np.array_equal(a, b)
+    for kw in (dict(n_corr=3), dict(n_corr=1, k_corr=0.001), dict(enable_vorticity=0), dict(enable_xsph=0),
+               dict(enable_vorticity=0, enable_xsph=0, iterations=5), dict(dt=0.008, gravity_y=-5.0, eps_relax=10.0, visc_c=0.01, vort_eps=0.01)):
+        gk = _gpu(rho0, **kw); gk.upload(pos, vel); gk.step(1)
+        ok = _oracle(rho0, 32, **kw); ok.upload(pos, vel); ok.step(1)
+        Pg, Vg, Rg = gk.download(); Po, Vo, Ro = ok.download()
+        assert np.array_equal(gk.neighbor_digest()[0], ok.digest()[0]), kw
+        _gate_whole_step(f"corner/{kw}", Pg, Rg, Po, Ro, rho0)
+        dv = np.linalg.norm(Vg - Vo, axis=1)
+        assert np.percentile(dv, 50) <= 1e-3, kw
+    bad = pos.copy(); bad[7, 1] = np.nan
+    gb = _gpu(rho0); gb.upload(bad, vel)
+    with pytest.raises(api.PbfError) as e:
+        gb.step(1)
+    assert e.value.code == api.PBF_ERR_DOMAIN
+    with pytest.raises(api.PbfError):                           # reference-order XSPH is not a GPU mode
+        _gpu(rho0, xsph_mode=1)
