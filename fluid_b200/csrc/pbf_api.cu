@@ -31,7 +31,7 @@ template <class T> cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc(
 }  // namespace
 int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   if (!(p.h > 0) || !(p.dt > 0) || !(p.rest_density > 0) || p.iterations < 0 || p.n_corr < 0) { err = "invalid PbfParams"; return PBF_ERR_INVALID; }
-  if (p.xsph_mode != PBF_XSPH_JACOBI) { err = "the GPU path implements PBF_XSPH_JACOBI only (SURVEY.md 7.3-3)"; return PBF_ERR_INVALID; }
+  if (p.xsph_mode != PBF_XSPH_JACOBI && p.xsph_mode != PBF_XSPH_REFERENCE_ORDER) { err = "unknown xsph_mode"; return PBF_ERR_INVALID; }
   volatile float h = (float)p.h;
   d.h = h; d.h2 = h * h; d.dt = (float)p.dt; d.inv_dt = 1.0f / d.dt;
   d.rho0 = (float)p.rest_density; d.inv_rho0 = 1.0f / d.rho0;

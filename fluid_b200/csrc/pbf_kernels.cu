@@ -554,6 +554,65 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
   pos[i] = make_float4(pi.x, pi.y, pi.z, 0.f);            // updatePosition (246-248)
 }
 
+// ------------------------------------------------------------------------------------------------
+// G'. validation mode PBF_XSPH_REFERENCE_ORDER.  The reference runs
+// updateVelocity + XSPH fused per particle in index order (particles.cpp:285-288, quirk Q11):
+// particle i sees V_j = final velocity for j < i and the STALE pre-solve velocity s_j for j > i
+// (original indices).  With u = (x* - x)/dt this is the strictly lower-triangular linear system
+//     v_i = u_i + C * sum_j (V_j - u_i) W_ij ,   V_j = v_j (j < i)  |  s_j (j > i)
+// solved here by fixed-point sweeps (contraction factor C*sum W ~ 0.7; every sweep makes one more
+// level of the dependency chain exact).  FINAL also produces omega_i = sum (V_j - u_i) x grad W and
+// the density.  Not on the performance path: three gathers per pair, ~48 sweeps.
+// ------------------------------------------------------------------------------------------------
+template <bool FINAL>
+__global__ void __launch_bounds__(TPB)
+k_xsph_reference(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs, const float4* __restrict__ u,
+                 const float4* __restrict__ stale, const float4* __restrict__ v_in, float4* __restrict__ v_out,
+                 const uint32_t* __restrict__ orig, float4* __restrict__ xs_w, float4* __restrict__ omega, float* __restrict__ rho_out,
+                 const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
+                 uint32_t sentinel, double* __restrict__ rho_sum) {
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  float rho = 0.f;
+  if (t < n) {
+    const uint32_t i = t;
+    const float4 pi = xs[i];
+    const float4 ui = u[i];
+    const uint32_t oi = orig[i];
+    float w3s = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+#define BODY_X(J)                                                                     \
+    {                                                                                 \
+      const uint32_t j_ = (J);                                                        \
+      const float4 pj = __ldg(&xs[j_]);                                               \
+      const bool done_ = j_ != sentinel && __ldg(&orig[j_]) < oi;                     \
+      const float4 vj = done_ ? v_in[j_] : __ldg(&stale[j_]);                         \
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;               \
+      const float ux = vj.x - ui.x, uy = vj.y - ui.y, uz = vj.z - ui.z;               \
+      float r2, w3, g;                                                                \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                           \
+      if (FINAL) {                                                                    \
+        ox = fmaf(g, uy * dz - uz * dy, ox);                                          \
+        oy = fmaf(g, uz * dx - ux * dz, oy);                                          \
+        oz = fmaf(g, ux * dy - uy * dx, oz);                                          \
+        w3s += w3;                                                                    \
+      }                                                                               \
+      sx = fmaf(w3, ux, sx); sy = fmaf(w3, uy, sy); sz = fmaf(w3, uz, sz);            \
+    }
+    PBF_FOR_NEIGHBORS(t, BODY_X)
+#undef BODY_X
+    const float xc = P.enable_xsph ? P.visc_c * P.poly6_c : 0.f;
+    v_out[i] = make_float4(fmaf(xc, sx, ui.x), fmaf(xc, sy, ui.y), fmaf(xc, sz, ui.z), 0.f);
+    if (FINAL) {
+      rho = P.poly6_c * w3s;
+      ox *= P.spiky_c; oy *= P.spiky_c; oz *= P.spiky_c;
+      const float on = sqrtf(ox * ox + oy * oy + oz * oz);
+      omega[i] = make_float4(ox, oy, oz, on);
+      xs_w[i] = make_float4(pi.x, pi.y, pi.z, on);
+      rho_out[i] = rho;
+    }
+  }
+  if (FINAL && rho_sum) block_sum_to_double(rho, rho_sum);
+}
+
 // load-time density: sum of poly6 over the frozen set INCLUDING self (particles.cpp:158-163,440-444)
 __global__ void __launch_bounds__(TPB)
 k_density_only(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
@@ -780,6 +839,27 @@ void enqueue_vorticity(Solver* h, int part) {
     LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_tmp, h->vtmp,
            h->vel[h->cur], h->omega, h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
 }
+// velocity + XSPH + vorticity in the reference's sequential order, by fixed-point sweeps (single GPU)
+void enqueue_vorticity_reference_order(Solver* h) {
+  const uint32_t n = h->r_cnt;
+  if (n == 0) return;
+  const int cur = h->cur, oth = cur ^ 1;
+  int sweeps = 48;
+  if (const char* e = getenv("PBF_XSPH_REF_SWEEPS")) sweeps = std::max(1, atoi(e));
+  float4* a = h->vel[oth];            // the other halves of the ping-pong buffers are free after the reorder
+  float4* b = h->pos[oth];
+  const float4* stale = h->vel[cur];  // pre-solve velocity (old v + gravity*dt): what j > i still holds in the reference
+  cudaMemcpyAsync(a, h->vtmp, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);     // v^(0) = u
+  for (int k = 0; k < sweeps; k++) {
+    LAUNCH(h, K_VORT_XSPH, k_xsph_reference<false>, blocks_for(n), h->dp, n, h->xs_a, h->vtmp, stale, a, b, h->orig[cur], (float4*)nullptr,
+           (float4*)nullptr, (float*)nullptr, h->nbr, h->slice_off, h->nbr_cnt, h->n_sorted, (double*)nullptr);
+    std::swap(a, b);
+  }
+  LAUNCH(h, K_VORT_XSPH, k_xsph_reference<true>, blocks_for(n), h->dp, n, h->xs_a, h->vtmp, stale, a, b, h->orig[cur], h->xs_tmp, h->omega,
+         h->rho, h->nbr, h->slice_off, h->nbr_cnt, h->n_sorted, &h->sc->rho_final);
+  cudaMemcpyAsync(h->vel[cur], b, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);  // only now may the stale velocities go
+}
+
 void enqueue_confine(Solver* h) {
   LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
          h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt);
@@ -833,7 +913,8 @@ void enqueue_step(Solver* h) {
   if (!enqueue_solve_fused(h))
     for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
   enqueue_velocity(h);
-  enqueue_vorticity(h, PART_ALL);
+  if (h->hp.xsph_mode == PBF_XSPH_REFERENCE_ORDER) enqueue_vorticity_reference_order(h);
+  else enqueue_vorticity(h, PART_ALL);
   enqueue_confine(h);
   h->steps_done++;
 }

@@ -164,6 +164,7 @@ int pbf_slab_configure(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int r
   if (h->n != 0 || h->cap != 0) return sfail(h, PBF_ERR_INVALID, "pbf_slab_configure must precede any upload");
   DevParams& d = h->dp;
   if (gx_lo < 0 || gx_hi > d.gdim_x_global || gx_hi <= gx_lo || halo_cap == 0) return sfail(h, PBF_ERR_INVALID, "bad slab range");
+  if (h->hp.xsph_mode != PBF_XSPH_JACOBI) return sfail(h, PBF_ERR_INVALID, "slab mode supports PBF_XSPH_JACOBI only (reference order is a global sequential dependency)");
   SCK(h, cudaSetDevice(h->device));
   d.gx_lo = gx_lo; d.gx_hi = gx_hi; d.cx_offset = gx_lo - 1;
   d.hop_left = left_cols; d.hop_right = right_cols;

@@ -39,7 +39,9 @@ enum {
 };
 
 /* XSPH ordering.  The reference applies updateVelocity + XSPH fused per
- * particle in index order (particles.cpp:285-288, quirk Q11); the parallel path is Jacobi. */
+ * particle in index order (particles.cpp:285-288, quirk Q11); the parallel path is Jacobi.
+ * REFERENCE_ORDER is a single-GPU validation mode: it reproduces the reference's velocities by
+ * fixed-point sweeps over the lower-triangular dependency (~10x the cost of the finalize pass). */
 enum { PBF_XSPH_JACOBI = 0, PBF_XSPH_REFERENCE_ORDER = 1 };
 
 /* Runtime parameters.  Defaults (pbf_default_params) are the reference's private macros,
@@ -61,7 +63,7 @@ typedef struct PbfParams {
   double box_max[3];    /* hard clamp upper                     {1,1.49,1}  particles.cpp:81-83 */
   double y_light;       /* virtual plane y (light)              1.49   particles.cpp:69,106  */
   double z_front;       /* virtual plane z (open front)         1.0    particles.cpp:60,97   */
-  int32_t xsph_mode;    /* PBF_XSPH_*; the GPU path implements JACOBI only                   */
+  int32_t xsph_mode;    /* PBF_XSPH_*; JACOBI is the performance path                        */
   int32_t enable_vorticity; /* 1: vorticity confinement (particles.cpp:236-244)              */
   int32_t enable_xsph;      /* 1: XSPH viscosity       (particles.cpp:229,233)               */
   int32_t reserved;
