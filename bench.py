@@ -296,9 +296,10 @@ def main():
             P = np.empty((n_local, 3)); V = np.empty((n_local, 3)); R = np.empty(n_local)
             solver.pin(P, V, R)          # the host arrays a caller reuses every step, page-locked once (pbf_host_register)
             solver.download_into(P, V, R)
+            solver.set_readback(P, V, R)   # each step streams its result into P, V, R (complete after sync)
             barrier(); t0 = time.perf_counter()
             for _ in range(k2):
-                solver.upload(P, V); solver.step(1, sync=False); solver.download_into(P, V, R)
+                solver.upload(P, V); solver.step(1, sync=True)
             torch.cuda.synchronize(); e_ms = (time.perf_counter() - t0) * 1e3
         else:
             capn = int(solver.particle_cap)
@@ -315,8 +316,8 @@ def main():
         e_ms = float(t[0])
         e2e = {"value": n_total * iters * k2 / (e_ms * 1e-3), "unit": "particle-iteration updates/s", "steps": k2,
                "h2d_bytes_per_step": n_total * (6 * 8 + (4 if world > 1 else 0)), "d2h_bytes_per_step": n_total * (7 * 8 + (4 if world > 1 else 0)), "ms_per_step": e_ms / k2,
-               "note": "host fp64 AoS buffers (pos, vel) uploaded and (pos, vel, density) read back EVERY step via pbf_upload/pbf_step/pbf_download "
-                       "(page-locked caller buffers, fp64 on the wire, fp64<->fp32 on the device); wall clock"}
+               "note": "host fp64 AoS buffers (pos, vel) uploaded (pbf_upload) and (pos, vel, density) read back EVERY step (streaming read-back "
+                       "pbf_set_readback at N=1, pbf_slab_download at N>1); page-locked caller buffers, fp64 on the wire, fp64<->fp32 on the device; wall clock"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.tank:

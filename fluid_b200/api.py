@@ -59,6 +59,7 @@ def load_library():
         "pbf_num_particles": (sz, [vp]),
         "pbf_host_register": (i32, [vp, vp, sz]),
         "pbf_host_unregister": (i32, [vp, vp]),
+        "pbf_set_readback": (i32, [vp, vp, vp, vp]),
         "pbf_step": (i32, [vp, i32]),
         "pbf_sync": (i32, [vp]),
         "pbf_estimate_densities": (i32, [vp]),
@@ -138,6 +139,11 @@ class Solver:
     def unpin(self, *arrays):
         for a in arrays:
             self._ck(self.lib.pbf_host_unregister(self.h, _ptr(a)))
+
+    def set_readback(self, P=None, V=None, R=None):
+        """Stream the results of every step() into these pinned arrays (complete after sync())."""
+        self._rb = (P, V, R)     # keep them alive
+        self._ck(self.lib.pbf_set_readback(self.h, _ptr(P), _ptr(V), _ptr(R)))
 
     def upload_device(self, n, d_pos_ptr, d_vel_ptr):
         self.n = n

@@ -150,6 +150,8 @@ int pbf::sync_and_check(Solver* hs) {
   pbf_handle* h = static_cast<pbf_handle*>(hs);
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaStreamSynchronize(h->stream));
+  if (h->copy_stream) CK(h, cudaStreamSynchronize(h->copy_stream));
+  h->rb_pending = false;
   CK(h, cudaGetLastError());
   if (h->call_timed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]); h->last_call_ms = ms; h->call_timed = false; }
   h->prof_collect();
@@ -245,6 +247,7 @@ void pbf_destroy(pbf_handle* h) {
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->block_sums); cudaFree(h->sc);
   if (h->ev_call[0]) cudaEventDestroy(h->ev_call[0]);
   if (h->ev_call[1]) cudaEventDestroy(h->ev_call[1]);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); for (int k = 0; k < 4; k++) if (h->ev_rb[k]) cudaEventDestroy(h->ev_rb[k]); }
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   {
@@ -327,6 +330,9 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   CK(h, cudaSetDevice(h->device));
   int rc = ensure_capacity(h, n);
   if (rc != PBF_OK) return rc;
+  if (h->copy_stream) CK(h, cudaStreamSynchronize(h->copy_stream));
+  h->rb_pending = false;
+  if (n != h->n) h->rb_pos = h->rb_vel = h->rb_rho = nullptr;          // read-back targets were sized for the old n
   h->n = n; h->cur = 0; h->have_neighbors = false; h->rebinned_at = -1;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   return io_upload(h, n, pos_xyz, vel_xyz);
@@ -351,7 +357,7 @@ int pbf_step(pbf_handle* h, int n_steps) {
   if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: drive the step through the pbf_slab_phase_* calls");
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaEventRecord(h->ev_call[0], h->stream));
-  for (int s = 0; s < n_steps; s++) enqueue_step(h);
+  for (int s = 0; s < n_steps; s++) enqueue_step(h, s == n_steps - 1);   // streaming read-back (if set) after the last step
   CK(h, cudaEventRecord(h->ev_call[1], h->stream));
   h->call_timed = true;
   if (n_steps > 0 && h->n > 0) h->have_neighbors = true;
@@ -435,6 +441,35 @@ int pbf_density_at(pbf_handle* h, size_t m, const double* query_xyz, double* den
   cudaFree(dq); cudaFree(dout);
   h->last_error = cudaGetErrorString(e);
   return PBF_ERR_CUDA;
+}
+
+// Streaming read-back: after this call every pbf_step() sends the results of its last step to these
+// page-locked (pbf_host_register) buffers on a second stream as soon as each becomes final —
+// positions when the solver iterations end, density after the vorticity/XSPH pass, velocity after
+// confinement — so most of the device-to-host time hides behind the finalize kernels.  pbf_sync()
+// completes the copies.  Pass NULLs to switch it off.  Single-GPU handles only.
+int pbf_set_readback(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density) {
+  if (!h) return PBF_ERR_INVALID;
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "pbf_set_readback is single-GPU only");
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  h->rb_pos = h->rb_vel = h->rb_rho = nullptr;
+  if (!pos_xyz && !vel_xyz && !density) return PBF_OK;
+  if (h->n == 0 || h->cap == 0) return fail(h, PBF_ERR_INVALID, "pbf_set_readback: upload particles first");
+  HandleExtra* x = extra_of(h);
+  const size_t n = h->n;
+  if ((pos_xyz && !x->registered(pos_xyz, 3 * n * sizeof(double))) || (vel_xyz && !x->registered(vel_xyz, 3 * n * sizeof(double))) ||
+      (density && !x->registered(density, n * sizeof(double))))
+    return fail(h, PBF_ERR_INVALID, "pbf_set_readback: buffers must be page-locked with pbf_host_register first");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, x->ensure_stage64(7 * h->cap));
+  h->rb_stage = x->stage64;
+  if (!h->copy_stream) {
+    CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) CK(h, cudaEventCreateWithFlags(&h->ev_rb[k], cudaEventDisableTiming));
+  }
+  h->rb_pos = pos_xyz; h->rb_vel = vel_xyz; h->rb_rho = density;
+  return PBF_OK;
 }
 
 // Page-lock caller-owned host buffers (cudaHostRegister) so that pbf_upload / pbf_download can DMA

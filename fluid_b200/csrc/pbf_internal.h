@@ -64,7 +64,13 @@ struct Solver {
   int fused_state = 0;               // 0 unknown, 1 cooperative fused iterations available, -1 not
   unsigned fused_grid = 0;
   bool have_neighbors = false;
-  long long rebinned_at = -1;        // steps_done when the arrays were last re-binned by committed position
+  long long rebinned_at = -1;
+  // streaming read-back (pbf_set_readback): results leave for page-locked host buffers as soon as each is final
+  double *rb_pos = nullptr, *rb_vel = nullptr, *rb_rho = nullptr;
+  double* rb_stage = nullptr;        // device staging, 7 doubles per particle (owned by pbf_api.cu)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_rb[4] = {nullptr, nullptr, nullptr, nullptr};   // positions final, density final, velocity final, copies done
+  bool rb_pending = false;        // steps_done when the arrays were last re-binned by committed position
 
   uint64_t launches = 0, steps_done = 0;
   double last_call_ms = 0.0;
@@ -97,7 +103,7 @@ struct Solver {
   }
 };
 
-void enqueue_step(Solver* h);
+void enqueue_step(Solver* h, bool readback = false);
 void enqueue_estimate_densities(Solver* h);
 void enqueue_predict_hash(Solver* h, int apply_forces);
 void enqueue_sort(Solver* h, size_t n_in);

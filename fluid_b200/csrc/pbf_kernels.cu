@@ -901,9 +901,25 @@ bool enqueue_solve_fused(Solver* h) {
 }
 
 // single-GPU step: every particle is owned, n never changes, nothing needs a host round trip
-void enqueue_step(Solver* h) {
+// one piece of the streaming read-back: wait (on the copy stream) until `ready` fires on the main stream,
+// scatter to original order as fp64 and DMA to the caller's page-locked buffer
+static void readback_piece(Solver* h, cudaEvent_t ready, int what) {
+  const size_t n = h->n;
+  cudaEventRecord(ready, h->stream);
+  cudaStream_t main_stream = h->stream;
+  cudaStreamWaitEvent(h->copy_stream, ready, 0);
+  h->stream = h->copy_stream;                               // LAUNCH() targets h->stream
+  if (what == 0 && h->rb_pos) { enqueue_export3_f64(h, h->xs_a, h->rb_stage); cudaMemcpyAsync(h->rb_pos, h->rb_stage, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream); }
+  if (what == 1 && h->rb_rho) { enqueue_export1_f64(h, h->rho, h->rb_stage + 6 * n); cudaMemcpyAsync(h->rb_rho, h->rb_stage + 6 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream); }
+  if (what == 2 && h->rb_vel) { enqueue_export3_f64(h, h->vel[h->cur], h->rb_stage + 3 * n); cudaMemcpyAsync(h->rb_vel, h->rb_stage + 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream); }
+  h->stream = main_stream;
+  if (what == 2) { cudaEventRecord(h->ev_rb[3], h->copy_stream); h->rb_pending = true; }
+}
+
+void enqueue_step(Solver* h, bool readback) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;
+  if (h->rb_pending) { cudaStreamWaitEvent(h->stream, h->ev_rb[3], 0); h->rb_pending = false; }   // copies still read xs_a / rho / vel
   cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);   // rho_first, rho_final
   h->r_i0 = 0; h->r_cnt = n; h->n_sorted = n;
   enqueue_predict_hash(h, 1);
@@ -912,10 +928,14 @@ void enqueue_step(Solver* h) {
   if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
   if (!enqueue_solve_fused(h))
     for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
+  readback = readback && h->copy_stream && (h->rb_pos || h->rb_vel || h->rb_rho);
+  if (readback) readback_piece(h, h->ev_rb[0], 0);          // positions are final once the iterations end
   enqueue_velocity(h);
   if (h->hp.xsph_mode == PBF_XSPH_REFERENCE_ORDER) enqueue_vorticity_reference_order(h);
   else enqueue_vorticity(h, PART_ALL);
+  if (readback) readback_piece(h, h->ev_rb[1], 1);          // density is final after the vorticity/XSPH pass
   enqueue_confine(h);
+  if (readback) readback_piece(h, h->ev_rb[2], 2);          // velocity last
   h->steps_done++;
 }
 

@@ -48,12 +48,14 @@ void Particles::ensureUploaded() {
            pbf_host_register(handle_, rho_.data(), n * sizeof(double)); }
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  if (n) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data());   // every step streams its result into the mirror
   uploaded_ = true;
 }
 
-void Particles::refreshMirror() {
+void Particles::refreshMirror(bool already_streamed) {
   const size_t n = ps.size();
-  int rc = pbf_download(handle_, pos_.data(), vel_.data(), rho_.data());
+  // after a step the streaming read-back has the data on its way: pbf_sync completes it
+  int rc = already_streamed ? pbf_sync(handle_) : pbf_download(handle_, pos_.data(), vel_.data(), rho_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] step failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   for (size_t i = 0; i < n; i++) {
     Particle* p = ps[i];
@@ -79,7 +81,7 @@ void Particles::timeStep(double delta_t) {
   simulate_time += delta_t;
   if (!quiet) std::cerr << " => " << simulate_time << std::endl;
   if (pbf_step(handle_, 1) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
-  refreshMirror();
+  refreshMirror(/*already_streamed=*/ps.size() > 0);
   double ms = 0;
   pbf_stats(handle_, &avg_rho_first_iter, &avg_rho_final, &ms);
   if (!quiet) std::cout << "avg rho: " << avg_rho_first_iter << " => " << avg_rho_final << std::endl;   // particles.cpp:267,279,295

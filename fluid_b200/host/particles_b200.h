@@ -70,7 +70,7 @@ struct Particles {
 
  private:
   void ensureUploaded();
-  void refreshMirror();
+  void refreshMirror(bool already_streamed = false);
   PbfParams params_;
   int device_;
   pbf_handle* handle_ = nullptr;

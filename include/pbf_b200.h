@@ -85,6 +85,10 @@ size_t pbf_num_particles(pbf_handle* h);
  * wire, conversion on the device).  Unregister, or destroy the handle, before freeing them. */
 int  pbf_host_register(pbf_handle* h, void* ptr, size_t bytes);
 int  pbf_host_unregister(pbf_handle* h, void* ptr);
+/* Streaming read-back into page-locked buffers: every pbf_step() then sends the state after its last
+ * step (what pbf_download would return) on a second stream as soon as each array is final, hidden
+ * behind the finalize kernels; pbf_sync() completes it.  NULLs switch it off. */
+int  pbf_set_readback(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 int  pbf_step(pbf_handle* h, int n_steps);      /* enqueues n_steps * timeStep(dt); asynchronous */

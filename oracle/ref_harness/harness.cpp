@@ -9,7 +9,9 @@
 //   * calls Particles::timeStep() (particles.cpp:250-301) and dumps state after each step.
 //
 // Usage: ref_harness (--xml file.xml | --bin file.bin) --steps S --out dump.bin [--quiet]
-//                    [--density-queries q.bin --density-out d.bin]
+//                    [--density-queries q.bin --density-out d.bin] [--sphere cx cy cz r]...
+//   --sphere  adds a StaticScene::Sphere obstacle to the BVH (the CBspheres scenes hold two r=0.3 spheres,
+//             dae/sky/CBspheres_lambertian.dae:291-305,575-594); repeatable.
 //   q.bin : int64 M, M*3 doubles; d.bin : M doubles = Particles::estimateDensityAt(q) after the last
 //           step (particles.cpp:446-453, the field marching cubes samples).
 //   .bin input : int64 N, double rho0 (already rounded through float like stof, Q17),
@@ -34,6 +36,8 @@
 #include "bvh.h"
 #include "particles.h"
 #include "static_scene/marching_triangle.h"
+#include "static_scene/object.h"
+#include "static_scene/sphere.h"
 
 using namespace CGL;
 using namespace CGL::StaticScene;
@@ -89,6 +93,7 @@ static void add_quad(std::vector<Primitive*>& prims, Vector3D a, Vector3D b, Vec
 int main(int argc, char** argv) {
   const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr;
   int steps = 1; bool quiet = false;
+  std::vector<double> spheres;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--xml" && i + 1 < argc) xml = argv[++i];
@@ -96,6 +101,7 @@ int main(int argc, char** argv) {
     else if (a == "--out" && i + 1 < argc) out = argv[++i];
     else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
     else if (a == "--quiet") quiet = true;
+    else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }
     else if (a == "--density-queries" && i + 1 < argc) dq = argv[++i];
     else if (a == "--density-out" && i + 1 < argc) dout = argv[++i];
     else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -120,6 +126,10 @@ int main(int argc, char** argv) {
   add_quad(prims, Vector3D(-1,1.5,-1), Vector3D(-1,0,-1), Vector3D(-1,0,1), Vector3D(-1,1.5,1), Vector3D(1,0,0));      // left
   add_quad(prims, Vector3D(1,1.5,1), Vector3D(1,0,1), Vector3D(1,0,-1), Vector3D(1,1.5,-1), Vector3D(-1,0,0));         // right
   add_quad(prims, Vector3D(1,1.5,-1), Vector3D(1,0,-1), Vector3D(-1,0,-1), Vector3D(-1,1.5,-1), Vector3D(0,0,1));      // back
+  for (size_t k = 0; k + 3 < spheres.size(); k += 4) {
+    SphereObject* so = new SphereObject(Vector3D(spheres[k], spheres[k+1], spheres[k+2]), spheres[k+3], nullptr);
+    for (Primitive* p : so->get_primitives()) prims.push_back(p);      // object.cpp:76-80 -> new Sphere(this, o, r)
+  }
   ps->bvh = new BVHAccel(prims);
 
   const int64_t n = (int64_t)ps->ps.size();
