@@ -275,14 +275,16 @@ def main():
                 e.update({"algorithmic_bytes_per_particle": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
             kernels[name] = e
     dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
-    traffic = None
+    traffic = None; ncu_note = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("particles") == n_local and dom in tj.get("kernels", {}):
             traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
+            ncu_note = {k: v for k, v in tj["kernels"][dom].items() if k != "dram_bytes_per_launch"}   # what ncu says binds it
+            ncu_note["source"] = tj.get("source")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
+                "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src, "ncu": ncu_note,
                 "algorithmic_bytes_per_launch": n_local * alg[dom], "avg_launch_ms": kernels[dom]["ms_per_launch"],
                 "whole_step": {"algorithmic_bytes_per_particle": BYTES_FIXED + (BYTES_LAMBDA + BYTES_DELTA) * iters,
                                "achieved": n_local * (BYTES_FIXED + (BYTES_LAMBDA + BYTES_DELTA) * iters) / (ms_per_step * 1e-3) / 1e9,
