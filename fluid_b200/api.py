@@ -45,7 +45,8 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # PBF_LIB: developer override for A/B runs against another build of the same ABI (never a CPU path)
+    path = os.environ.get("PBF_LIB") or _build.build()
     lib = C.CDLL(path)
     vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
     sig = {
