@@ -242,6 +242,7 @@ void pbf_destroy(pbf_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->prof_collect();
+  h->graph_invalidate();
   for (auto e : h->event_pool) cudaEventDestroy(e);
   free_arrays(h);
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->block_sums); cudaFree(h->sc);
@@ -333,6 +334,7 @@ int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel
   if (h->copy_stream) CK(h, cudaStreamSynchronize(h->copy_stream));
   h->rb_pending = false;
   if (n != h->n) h->rb_pos = h->rb_vel = h->rb_rho = nullptr;          // read-back targets were sized for the old n
+  h->graph_invalidate();                              // grids and buffers are baked into the captured step
   h->n = n; h->cur = 0; h->have_neighbors = false; h->rebinned_at = -1;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   return io_upload(h, n, pos_xyz, vel_xyz);
@@ -344,6 +346,7 @@ int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const flo
   int rc = ensure_capacity(h, n);
   if (rc != PBF_OK) return rc;
   if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
+  h->graph_invalidate();
   h->n = n; h->cur = 0; h->have_neighbors = false;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   enqueue_import(h, d_pos_xyz, d_vel_xyz);
@@ -352,12 +355,43 @@ int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const flo
   return PBF_OK;
 }
 
+// CUDA-graph replay of the step (see Solver::graph_exec): single GPU, no per-kernel profiling (its events would be
+// captured), no streaming read-back (it runs on a second stream only after the last step of a call).
+static bool step_uses_graph(pbf_handle* h) {
+  if (h->slab || h->profiling || h->n == 0 || h->rb_pos || h->rb_vel || h->rb_rho) return false;
+  if (h->graph_policy < 0) {
+    const char* e = getenv("PBF_GRAPH");
+    h->graph_policy = e ? (atoi(e) != 0) : (h->n <= (1u << 18));
+  }
+  return h->graph_policy == 1;
+}
+
 int pbf_step(pbf_handle* h, int n_steps) {
   if (!h || n_steps < 0) return fail(h, PBF_ERR_INVALID, "pbf_step: bad argument");
   if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: drive the step through the pbf_slab_phase_* calls");
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaEventRecord(h->ev_call[0], h->stream));
-  for (int s = 0; s < n_steps; s++) enqueue_step(h, s == n_steps - 1);   // streaming read-back (if set) after the last step
+  if (step_uses_graph(h)) {
+    for (int s = 0; s < n_steps; s++) {
+      const int par = h->cur;
+      if (!h->graph_exec[par]) {                       // first step with this buffer parity: capture instead of launching
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = h->launches;
+        CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_step(h, false);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        h->cur = par; h->steps_done--;                 // capturing ran nothing: undo the host-side bookkeeping
+        h->graph_launches[par] = h->launches - l0; h->launches = l0;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&h->graph_exec[par], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess) { cudaGetLastError(); h->graph_exec[par] = nullptr; h->graph_policy = 0; enqueue_step(h, false); continue; }
+      }
+      CK(h, cudaGraphLaunch(h->graph_exec[par], h->stream));
+      h->cur = par ^ 1; h->steps_done++; h->launches += h->graph_launches[par];
+    }
+  } else {
+    for (int s = 0; s < n_steps; s++) enqueue_step(h, s == n_steps - 1);   // streaming read-back (if set) after the last step
+  }
   CK(h, cudaEventRecord(h->ev_call[1], h->stream));
   h->call_timed = true;
   if (n_steps > 0 && h->n > 0) h->have_neighbors = true;
@@ -496,6 +530,7 @@ int pbf_host_unregister(pbf_handle* h, void* ptr) {
 int pbf_debug_capture(pbf_handle* h, int on) {
   if (!h) return PBF_ERR_INVALID;
   h->capture_xpred = on ? 1 : 0;
+  h->graph_invalidate();
   if (on && !h->xpred && h->cap) CK(h, dmalloc(&h->xpred, h->cap));
   return PBF_OK;
 }

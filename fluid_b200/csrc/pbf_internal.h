@@ -72,6 +72,17 @@ struct Solver {
   cudaEvent_t ev_rb[4] = {nullptr, nullptr, nullptr, nullptr};   // positions final, density final, velocity final, copies done
   bool rb_pending = false;        // steps_done when the arrays were last re-binned by committed position
 
+  // Launch-bound scenes (the reference's own p.xml / spheres_p.xml: 720 / 2106 particles, 36 launches of a few
+  // microseconds each): the step's launch sequence is captured once per buffer parity (`cur` flips every
+  // step) into a CUDA graph and replayed.  PBF_GRAPH=0/1 overrides the size policy (on up to 2^18 particles).
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  uint64_t graph_launches[2] = {0, 0};   // kernels inside each captured step (what launch_count() advances by per replay)
+  int graph_policy = -1;                 // -1 not decided yet, 0 plain launches, 1 graphs
+  void graph_invalidate() {
+    for (int k = 0; k < 2; k++) if (graph_exec[k]) { cudaGraphExecDestroy(graph_exec[k]); graph_exec[k] = nullptr; }
+    graph_policy = -1;
+  }
+
   uint64_t launches = 0, steps_done = 0;
   double last_call_ms = 0.0;
   cudaEvent_t ev_call[2] = {nullptr, nullptr};

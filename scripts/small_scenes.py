@@ -13,16 +13,21 @@ for name, iters, steps in (("p", 12, 63), ("spheres_p", 4, 63), ("spheres_p", 12
     pos, vel, rho0 = sc["pos"], sc["vel"], float(sc["rho0"])
     n = len(pos)
     row = {"scene": name, "n": n, "iterations": iters, "steps": steps}
-    for fused in ("0", "1"):
-        os.environ["PBF_FUSED"] = fused
+    for graph in ("0", "1"):
+        os.environ["PBF_GRAPH"] = graph          # 1 (the default for small scenes) = replay the step's launches as one CUDA graph
         g = api.Solver(api.default_params(rest_density=rho0, iterations=iters))
         g.upload(pos, vel); g.step(5)
         g.upload(pos, vel)
         t0 = time.perf_counter(); g.step(steps); wall = time.perf_counter() - t0
         ms = g.stats()[2]
-        row[f"gpu_ms_per_step_fused{fused}"] = ms / steps
-        row[f"gpu_wall_ms_per_step_fused{fused}"] = 1e3 * wall / steps
-        row[f"gpu_updates_per_s_fused{fused}"] = n * iters * steps / (ms * 1e-3)
+        # the host adapter's pattern: one step + read-back per frame (Particles::timeStep, then redraw reads ps)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            g.step(1); g.download()
+        row[f"gpu_wall_ms_per_step_with_download_graph{graph}"] = 1e3 * (time.perf_counter() - t0) / steps
+        row[f"gpu_ms_per_step_graph{graph}"] = ms / steps
+        row[f"gpu_wall_ms_per_step_graph{graph}"] = 1e3 * wall / steps
+        row[f"gpu_updates_per_s_graph{graph}"] = n * iters * steps / (ms * 1e-3)
     # CPU: oracle port (fp64, grid, all cores) and, for 12 iterations, the unmodified reference
     o = H.Oracle(H.default_params(rest_density=rho0, iterations=iters, xsph_mode=H.XSPH_JACOBI), 64, H.COLLIDE_BOX, H.SEARCH_GRID)
     o.upload(pos, vel); t0 = time.perf_counter(); o.step(steps); dt = time.perf_counter() - t0

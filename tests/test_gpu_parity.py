@@ -354,6 +354,29 @@ def test_density_field_vs_reference_and_oracle(name):
         assert np.array_equal(a, b)
 
 
+def test_graph_replay_equals_plain_launches(monkeypatch):
+    """Launch-bound scenes replay the step as a CUDA graph (one per buffer parity, PBF_GRAPH): the state after
+    7 steps, a re-upload and 3 more steps is bit-identical to plain launches, and launch_count() still counts
+    every kernel of every replayed step."""
+    pos, vel, rho0, _ = _scene("two_blocks")
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PBF_GRAPH", mode)
+        g = _gpu(rho0); g.upload(pos, vel)
+        g.step(1); g.step(4); g.step(2)                        # both parities, several replays per call
+        a = g.download()
+        g.estimate_densities()                                 # flips the buffer parity outside a step
+        g.step(2)
+        b = g.download()
+        g.upload(pos[:700], vel[:700]); g.step(3)              # another size: graphs are rebuilt
+        out[mode] = (a, b, g.download(), g.launch_count(), g.neighbor_digest())
+    for k in range(3):
+        for x, y in zip(out["0"][k], out["1"][k]):
+            assert np.array_equal(x, y)
+    assert out["0"][3] == out["1"][3] and out["0"][3] >= 12 * 36
+    assert np.array_equal(out["0"][4][0], out["1"][4][0])
+
+
 def test_edge_cases_and_parameter_variants():
     """Empty / single-particle inputs, re-upload with another size, non-default solver parameters
     (n_corr != 4 takes the generic exponent path; vorticity / XSPH switched off), two handles at once,
