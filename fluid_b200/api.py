@@ -61,6 +61,7 @@ def load_library():
         "pbf_host_register": (i32, [vp, vp, sz]),
         "pbf_host_unregister": (i32, [vp, vp]),
         "pbf_set_readback": (i32, [vp, vp, vp, vp]),
+        "pbf_set_obstacle_spheres": (i32, [vp, sz, vp]),
         "pbf_step": (i32, [vp, i32]),
         "pbf_sync": (i32, [vp]),
         "pbf_estimate_densities": (i32, [vp]),
@@ -145,6 +146,11 @@ class Solver:
         """Stream the results of every step() into these pinned arrays (complete after sync())."""
         self._rb = (P, V, R)     # keep them alive
         self._ck(self.lib.pbf_set_readback(self.h, _ptr(P), _ptr(V), _ptr(R)))
+
+    def set_obstacle_spheres(self, spheres):
+        """Obstacle spheres of the collision scene, rows (cx, cy, cz, r); an empty list removes them."""
+        sp = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        self._ck(self.lib.pbf_set_obstacle_spheres(self.h, sp.shape[0], _ptr(sp)))
 
     def upload_device(self, n, d_pos_ptr, d_vel_ptr):
         self.n = n

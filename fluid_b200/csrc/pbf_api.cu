@@ -62,6 +62,8 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.yl = (float)p.y_light; d.zf = (float)p.z_front;
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
+  d.n_sph = 0;
+  for (int k = 0; k < PBF_MAX_SPHERES; k++) { d.sph[k] = make_float4(0.f, 0.f, 0.f, 0.f); d.sph_r2[k] = 0.f; }
   return PBF_OK;
 }
 namespace {
@@ -356,9 +358,9 @@ int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const flo
 }
 
 // CUDA-graph replay of the step (see Solver::graph_exec): single GPU, no per-kernel profiling (its events would be
-// captured), no streaming read-back (it runs on a second stream only after the last step of a call).
+// captured).  A streaming read-back, if set, follows the last replayed step as plain launches.
 static bool step_uses_graph(pbf_handle* h) {
-  if (h->slab || h->profiling || h->n == 0 || h->rb_pos || h->rb_vel || h->rb_rho) return false;
+  if (h->slab || h->profiling || h->n == 0) return false;
   if (h->graph_policy < 0) {
     const char* e = getenv("PBF_GRAPH");
     h->graph_policy = e ? (atoi(e) != 0) : (h->n <= (1u << 18));
@@ -373,6 +375,7 @@ int pbf_step(pbf_handle* h, int n_steps) {
   CK(h, cudaEventRecord(h->ev_call[0], h->stream));
   if (step_uses_graph(h)) {
     for (int s = 0; s < n_steps; s++) {
+      if (h->rb_pending) { cudaStreamWaitEvent(h->stream, h->ev_rb[3], 0); h->rb_pending = false; }   // copies still read xs_a / rho / vel
       const int par = h->cur;
       if (!h->graph_exec[par]) {                       // first step with this buffer parity: capture instead of launching
         cudaGraph_t g = nullptr;
@@ -389,6 +392,7 @@ int pbf_step(pbf_handle* h, int n_steps) {
       CK(h, cudaGraphLaunch(h->graph_exec[par], h->stream));
       h->cur = par ^ 1; h->steps_done++; h->launches += h->graph_launches[par];
     }
+    if (n_steps > 0) enqueue_readback_all(h);
   } else {
     for (int s = 0; s < n_steps; s++) enqueue_step(h, s == n_steps - 1);   // streaming read-back (if set) after the last step
   }
@@ -396,6 +400,25 @@ int pbf_step(pbf_handle* h, int n_steps) {
   h->call_timed = true;
   if (n_steps > 0 && h->n > 0) h->have_neighbors = true;
   CK(h, cudaGetLastError());
+  return PBF_OK;
+}
+
+// Obstacle spheres of the collision scene (the reference keeps them as StaticScene::Sphere primitives in
+// Particles::bvh).  Kernel parameters carry them, so captured graphs are rebuilt.
+int pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* s) {
+  if (!h || (count && !s)) return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_spheres: null argument");
+  if (count > PBF_MAX_SPHERES) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_spheres: more than PBF_MAX_SPHERES spheres");
+  for (size_t k = 0; k < count; k++)
+    if (!(s[4 * k + 3] > 0) || !std::isfinite(s[4 * k]) || !std::isfinite(s[4 * k + 1]) || !std::isfinite(s[4 * k + 2]) || !std::isfinite(s[4 * k + 3]))
+      return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_spheres: radius must be positive and all values finite");
+  h->graph_invalidate();
+  h->dp.n_sph = (int)count;
+  for (size_t k = 0; k < count; k++) {
+    volatile float r = (float)s[4 * k + 3];
+    volatile float r2 = r * r;                         // one fp32 rounding, like Oracle<float>::set_spheres
+    h->dp.sph[k] = make_float4((float)s[4 * k], (float)s[4 * k + 1], (float)s[4 * k + 2], r);
+    h->dp.sph_r2[k] = r2;
+  }
   return PBF_OK;
 }
 

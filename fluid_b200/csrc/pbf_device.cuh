@@ -31,6 +31,10 @@ struct DevParams {
   // position maps to the same cell everywhere); this rank stores columns cx_offset .. cx_offset+gdim[0]-1
   // and owns the global columns [gx_lo, gx_hi).  Single GPU: cx_offset 0, owns everything.
   int   gdim_x_global, cx_offset, gx_lo, gx_hi, hop_left, hop_right;
+  // obstacle spheres (pbf_set_obstacle_spheres): centre xyz, radius in .w; r^2 = r*r rounded once
+  int   n_sph;
+  float4 sph[8];
+  float sph_r2[8];
 };
 
 // ---- EXACT regime -------------------------------------------------------------------------------
@@ -68,6 +72,42 @@ __device__ __forceinline__ bool ex_box_hit(const DevParams& P, float3 o, float3 
   return hit;
 }
 
+// One-sided obstacle spheres: a sphere blocks only motion INTO it (d . (o - c) < 0), the entry root is clamped to
+// t >= 0 and an origin on or inside the surface is in contact now (t = 0).  For an origin outside the sphere this
+// is the reference's Sphere::test (sphere.cpp:10-41).  `skip` = the sphere being slid on.  Mirrors
+// Oracle<float>::sphere_hit_onesided operation for operation.
+__device__ __forceinline__ float ex_dot(float3 a, float3 b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ bool ex_sphere_hit(const DevParams& P, float3 o, float3 d, float& max_t, int& which, float3& nrm, int skip) {
+  bool hit = false;
+  for (int k = 0; k < P.n_sph; k++) {
+    if (k == skip) continue;
+    const float4 S = P.sph[k];
+    const float3 m = make_float3(__fsub_rn(o.x, S.x), __fsub_rn(o.y, S.y), __fsub_rn(o.z, S.z));
+    const float b = __fmul_rn(2.f, ex_dot(m, d));
+    if (!(b < 0.f)) continue;
+    const float c = __fsub_rn(ex_dot(m, m), P.sph_r2[k]);
+    float t;
+    if (c <= 0.f) t = 0.f;
+    else {
+      const float a = ex_dot(d, d);
+      const float delta = __fsub_rn(__fmul_rn(b, b), __fmul_rn(__fmul_rn(4.f, a), c));
+      if (delta < 0.f) continue;
+      t = __fdiv_rn(__fsub_rn(-b, __fsqrt_rn(delta)), __fmul_rn(2.f, a));
+      if (t < 0.f) t = 0.f;
+    }
+    if (t <= max_t) {
+      max_t = t; which = k; hit = true;
+      const float3 nn = make_float3(__fsub_rn(__fadd_rn(o.x, __fmul_rn(t, d.x)), S.x), __fsub_rn(__fadd_rn(o.y, __fmul_rn(t, d.y)), S.y),
+                                    __fsub_rn(__fadd_rn(o.z, __fmul_rn(t, d.z)), S.z));
+      const float rn = __fdiv_rn(1.f, __fsqrt_rn(ex_norm2(nn.x, nn.y, nn.z)));
+      nrm = make_float3(__fmul_rn(rn, nn.x), __fmul_rn(rn, nn.y), __fmul_rn(rn, nn.z));
+    }
+  }
+  return hit;
+}
+
 // Swept move of p by delta against the box: clamp() (respond=false, particles.cpp:51-84) and
 // clamp_response() (respond=true: slide once along the wall, particles.cpp:87-132), with the
 // fp32 contact rules of SURVEY.md §7.3-4 (one-sided planes, exact axis normals, sticky virtual
@@ -81,24 +121,33 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
     bool virt = false;
     if (d.z > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.zf, p.z), d.z); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
     if (d.y > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.yl, p.y), d.y); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
-    float max_t = l; int axis = -1, side = 0;
-    const bool hit = ex_box_hit(P, p, d, max_t, axis, side, -1, 0);
+    float max_t = l; int axis = -1, side = 0, sph = -1;
+    float3 sn = make_float3(0.f, 0.f, 0.f);
+    bool hit = ex_box_hit(P, p, d, max_t, axis, side, -1, 0);
+    if (P.n_sph > 0 && ex_sphere_hit(P, p, d, max_t, sph, sn, -1)) hit = true;   // nearest of walls and spheres
     if (hit || virt) {
       const float s = __fsub_rn(max_t, P.eps_d);
       p.x = __fadd_rn(p.x, __fmul_rn(s, d.x));
       p.y = __fadd_rn(p.y, __fmul_rn(s, d.y));
       p.z = __fadd_rn(p.z, __fmul_rn(s, d.z));
       if (respond && hit && !virt) {
-        const float dn = side ? -comp(d, axis) : comp(d, axis);
-        float3 tg = delta;
-        if (axis == 0) tg.x = 0.f; else if (axis == 1) tg.y = 0.f; else tg.z = 0.f;
+        float dn; float3 tg = delta;
+        if (sph >= 0) {                                  // radial normal; tangent = delta - (delta . n) n
+          dn = ex_dot(d, sn);
+          const float dd = ex_dot(delta, sn);
+          tg = make_float3(__fsub_rn(delta.x, __fmul_rn(dd, sn.x)), __fsub_rn(delta.y, __fmul_rn(dd, sn.y)), __fsub_rn(delta.z, __fmul_rn(dd, sn.z)));
+        } else {
+          dn = side ? -comp(d, axis) : comp(d, axis);
+          if (axis == 0) tg.x = 0.f; else if (axis == 1) tg.y = 0.f; else tg.z = 0.f;
+        }
         const float t2 = ex_norm2(tg.x, tg.y, tg.z);
         if (dn > -1.f && t2 > 0.f) {
           const float rn = __fdiv_rn(1.f, __fsqrt_rn(t2));
           float3 d2 = make_float3(__fmul_rn(rn, tg.x), __fmul_rn(rn, tg.y), __fmul_rn(rn, tg.z));
           float mt = __fmul_rn(__fsub_rn(total_l, max_t), 0.5f);
-          int a2 = -1, s2 = 0;
-          ex_box_hit(P, p, d2, mt, a2, s2, axis, side);
+          int a2 = -1, s2 = 0, k2 = -1; float3 n2;
+          ex_box_hit(P, p, d2, mt, a2, s2, sph >= 0 ? -1 : axis, side);     // the surface being slid on is never re-tested
+          if (P.n_sph > 0) ex_sphere_hit(P, p, d2, mt, k2, n2, sph);
           const float s3 = __fsub_rn(mt, P.eps_d);
           p.x = __fadd_rn(p.x, __fmul_rn(s3, d2.x));
           p.y = __fadd_rn(p.y, __fmul_rn(s3, d2.y));

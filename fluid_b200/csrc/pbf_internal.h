@@ -115,6 +115,7 @@ struct Solver {
 };
 
 void enqueue_step(Solver* h, bool readback = false);
+void enqueue_readback_all(Solver* h);
 void enqueue_estimate_densities(Solver* h);
 void enqueue_predict_hash(Solver* h, int apply_forces);
 void enqueue_sort(Solver* h, size_t n_in);

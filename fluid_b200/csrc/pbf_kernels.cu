@@ -916,6 +916,12 @@ static void readback_piece(Solver* h, cudaEvent_t ready, int what) {
   if (what == 2) { cudaEventRecord(h->ev_rb[3], h->copy_stream); h->rb_pending = true; }
 }
 
+// all three pieces at once, after a complete step (the graph-replay path of launch-bound scenes: nothing to hide behind)
+void enqueue_readback_all(Solver* h) {
+  if (!h->copy_stream || h->n == 0 || !(h->rb_pos || h->rb_vel || h->rb_rho)) return;
+  for (int what = 0; what < 3; what++) readback_piece(h, h->ev_rb[what], what);
+}
+
 void enqueue_step(Solver* h, bool readback) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;

@@ -46,6 +46,9 @@ void Particles::ensureUploaded() {
   // the mirror arrays live as long as the handle: page-lock them once so every step's read-back is a direct DMA
   if (n) { pbf_host_register(handle_, pos_.data(), 3 * n * sizeof(double)); pbf_host_register(handle_, vel_.data(), 3 * n * sizeof(double));
            pbf_host_register(handle_, rho_.data(), n * sizeof(double)); }
+  if (!spheres_.empty() && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
+    std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
+  }
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   if (n) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data());   // every step streams its result into the mirror
@@ -69,6 +72,13 @@ void Particles::estimateDensities() {
   ensureUploaded();
   if (pbf_estimate_densities(handle_) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   refreshMirror();
+}
+
+void Particles::setObstacleSpheres(const std::vector<double>& s) {
+  spheres_ = s;
+  if (handle_ && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
+    std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
+  }
 }
 
 void Particles::timeStep(double delta_t) {

@@ -59,6 +59,10 @@ struct Particles {
   void timeStep(double delta_t);                 // particles.cpp:250-297 (delta_t must equal params.dt)
   void timeStep();                               // particles.cpp:299-301
   void estimateDensities();                      // particles.cpp:440-444
+  // The reference collides against `BVHAccel* bvh` (particles.h:108, set by pathtracer.cpp:266).  Of that scene the
+  // GPU step takes the box (PbfParams) and the StaticScene::Sphere primitives: rows (cx, cy, cz, r), at most
+  // PBF_MAX_SPHERES.  May be called at any time; takes effect from the next timeStep().
+  void setObstacleSpheres(const std::vector<double>& cx_cy_cz_r);
   double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
   // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
   std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);
@@ -75,7 +79,7 @@ struct Particles {
   int device_;
   pbf_handle* handle_ = nullptr;
   bool uploaded_ = false;
-  std::vector<double> pos_, vel_, rho_;
+  std::vector<double> pos_, vel_, rho_, spheres_;
 };
 
 // Application::load_particles (application.cpp:302-344): <particles><density>rho0</density><ps>

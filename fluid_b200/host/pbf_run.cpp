@@ -3,6 +3,7 @@
 //   load_particles -> estimateDensities -> while (simulate_time < T) timeStep()   (63 steps / second, Q18)
 // Optional --dump writes the per-step state in the same PBFDUMP1 format as oracle/ref_harness.
 //   pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--iterations I]
+//           [--sphere cx cy cz r]...      obstacle spheres of the collision scene (the CBspheres scenes hold two)
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -18,6 +19,7 @@ using namespace pbfhost;
 int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
+  std::vector<double> spheres;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-p" && i + 1 < argc) pfile = argv[++i];
@@ -25,9 +27,10 @@ int main(int argc, char** argv) {
     else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
     else if (a == "--iterations" && i + 1 < argc) iterations = atoi(argv[++i]);
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
+    else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }   // obstacle sphere cx cy cz r, repeatable
     else if (a == "--quiet") quiet = true;
     else if (a == "--parse-only") parse_only = true;
-    else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only]\n"); return 2; }
+    else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--sphere cx cy cz r]...\n"); return 2; }
   }
   if (!pfile) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
   std::string err;
@@ -47,6 +50,7 @@ int main(int argc, char** argv) {
   if (!ps) { printf("[ERROR] XML error: %s\n", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
   printf("Done!\n");
   ps->quiet = quiet;
+  if (!spheres.empty()) ps->setObstacleSpheres(spheres);
   const int64_t n = (int64_t)ps->ps.size();
   if (steps < 0 && seconds < 0) steps = 1;
   FILE* f = dump ? fopen(dump, "wb") : nullptr;

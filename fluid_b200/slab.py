@@ -153,6 +153,10 @@ class SlabSolver:
             raise api.PbfError(rc, self.lib.pbf_last_error(self.h).decode())
 
     # -- setup ---------------------------------------------------------------------------------------
+    def set_obstacle_spheres(self, spheres):
+        """Obstacle spheres (rows cx, cy, cz, r): global scene data, call with the same list on every rank."""
+        self.solver.set_obstacle_spheres(spheres)
+
     def columns_of(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         col = np.empty(pos.shape[0], dtype=np.int32)

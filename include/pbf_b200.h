@@ -77,6 +77,15 @@ void pbf_destroy(pbf_handle* h);
 const char* pbf_last_error(pbf_handle* h);      /* valid until the next call on h            */
 int  pbf_device_count(void);                    /* 0 when no CUDA device is visible          */
 
+/* ---- collision scene beyond the box ------------------------------------------------------- */
+/* Obstacle spheres, rows (cx, cy, cz, r): the StaticScene::Sphere primitives of the BVH the reference collides
+ * against (Particles::bvh, particles.cpp:76,112-122; sphere.cpp:10-76), e.g. the two r = 0.3 spheres of the
+ * CBspheres scenes.  Replaces the previous set; count 0 removes them; at most PBF_MAX_SPHERES.  Takes effect
+ * from the next pbf_step.  Rules: nearest hit of walls and spheres, a sphere blocks only motion
+ * into it, one slide along the tangent in the predict pass. */
+#define PBF_MAX_SPHERES 8
+int  pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* cx_cy_cz_r);
+
 /* ---- state in / out (host buffers, original order, doubles) ----------------------------- */
 int  pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz);
 int  pbf_download(pbf_handle* h, double* pos_xyz, double* vel_xyz, double* density); /* syncs; any pointer may be NULL */

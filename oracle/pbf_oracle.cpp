@@ -45,6 +45,11 @@ void oracle_destroy(void* hv) {
   delete h->f; delete h->d; delete h;
 }
 
+// obstacle spheres (cx, cy, cz, r) x count; literal mode rebuilds the reference's BVH over walls + spheres
+void oracle_set_spheres(void* hv, size_t count, const double* cxcyczr) {
+  visit((Handle*)hv, [&](auto& o) { o.set_spheres(count, cxcyczr); return 0; });
+}
+
 void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int oracle_max_threads() { return omp_get_max_threads(); }
 

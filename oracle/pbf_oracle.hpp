@@ -71,6 +71,10 @@ enum { SEARCH_BRUTE = 0, SEARCH_GRID = 1 };
 // ---- wall triangles of the reference scene (dae/sky/CBempty.dae:229-444 as exact quads) --------
 template <class R>
 struct Tri { V3<R> p1, p2, p3, n; };
+// ---- obstacle sphere (static_scene/sphere.h:23-24: r2 = r*r), e.g. the two r = 0.3 spheres of the
+// CBspheres scenes (dae/sky/CBspheres_lambertian.dae:291-305,575-594) -------------------------------------------
+template <class R>
+struct Sph { V3<R> c; R r, r2; };
 
 template <class R>
 struct Oracle {
@@ -82,6 +86,7 @@ struct Oracle {
   int NCORR, ITERS;
   V bmin, bmax; R YL, ZF;
   std::vector<Tri<R>> tris;
+  std::vector<Sph<R>> spheres;
 
   size_t n = 0;
   std::vector<V> pos, npos, vel, vort, xpred;
@@ -102,6 +107,7 @@ struct Oracle {
     // particles.cpp:151  tensile_instability_scale = 1 / poly6(0,0,0.1*H)
     TSCALE = R(1) / poly6(V(R(0), R(0), R(p.dq_ratio) * H));
     build_walls();
+    build_bvh();
   }
 
   void add_quad(V a, V b, V c, V d, V nn) {
@@ -149,14 +155,134 @@ struct Oracle {
     if (nrm) *nrm = w * T.n + u * T.n + v * T.n;
     return true;
   }
-  // nearest hit (bvh.cpp:165-192 visits every primitive the boxes let through; each hit shrinks
-  // max_t) and any hit (bvh.cpp:142-163).  Inside the convex box a segment meets at most one
-  // wall, so box culling and visiting order cannot change the answer; verified bit-exactly
-  // against the compiled reference.
-  bool scene_hit(const V& o, const V& d, R& max_t, V* nrm) const {
-    bool hit = false;
-    for (const Tri<R>& T : tris) if (tri_hit(T, o, d, max_t, nrm)) { hit = true; if (!nrm) return true; }
+  // ---- ray / sphere, literal (static_scene/sphere.cpp:10-41,43-76), segment [0, max_t] ----------------------
+  // Quirk kept: when the near root is out of range the FAR root is accepted, so a ray that starts inside
+  // a sphere "hits" the surface from within.
+  bool sphere_hit_literal(const Sph<R>& S, const V& o, const V& d, R& max_t, V* nrm) const {
+    R a = dot(d, d);
+    V m = o - S.c;
+    R b = R(2) * dot(m, d);
+    R c = dot(m, m) - S.r2;
+    R delta = b * b - R(4) * a * c;
+    if (delta < R(0)) return false;
+    R t = (-b - std::sqrt(delta)) / (R(2) * a), t1;
+    if ((t >= R(0)) && (t <= max_t)) t1 = t;
+    else {
+      t = (-b + std::sqrt(delta)) / (R(2) * a);
+      if ((t >= R(0)) && (t <= max_t)) t1 = t; else return false;
+    }
+    max_t = t1;
+    if (nrm) { V nn = o + t1 * d - S.c; *nrm = nn.unit(); }
+    return true;
+  }
+
+  // ---- the reference's BVH (bvh.cpp:48-142, bbox.h:29-122, bbox.cpp:10-30), restated so that primitives are
+  // visited in the reference's own order.  The order matters with obstacles: clamp() uses the ANY-hit query
+  // (particles.cpp:76, bvh.cpp:142-163), which returns the first primitive found, not the nearest one.
+  struct Box {
+    V mn, mx, ext;
+    Box() : mn(inf(), inf(), inf()), mx(-inf(), -inf(), -inf()) { ext = mx - mn; }
+    explicit Box(const V& p) : mn(p), mx(p) { ext = mx - mn; }
+    Box(const V& a, const V& b) : mn(a), mx(b) { ext = mx - mn; }
+    static R inf() { return std::numeric_limits<R>::infinity(); }
+    void expand(const Box& b) {
+      mn.x = rmin(mn.x, b.mn.x); mn.y = rmin(mn.y, b.mn.y); mn.z = rmin(mn.z, b.mn.z);
+      mx.x = rmax(mx.x, b.mx.x); mx.y = rmax(mx.y, b.mx.y); mx.z = rmax(mx.z, b.mx.z);
+      ext = mx - mn;
+    }
+    void expand(const V& p) { expand(Box(p)); }
+    V centroid() const { return (mn + mx) / R(2); }
+    R area() const {
+      if (mn.x > mx.x || mn.y > mx.y || mn.z > mx.z) return R(0);
+      return R(2) * (ext.x * ext.z + ext.x * ext.y + ext.y * ext.z);
+    }
+    bool hit(const V& o, const V& d, R& t0, R& t1) const {   // bbox.cpp:10-30 (division by a zero component included)
+      R tmin = -inf(), tmax = inf();
+      for (int i = 0; i < 3; i++) {
+        R ta = (mn[i] - o[i]) / d[i], tb = (mx[i] - o[i]) / d[i];
+        if (ta > tb) { R tt = tb; tb = ta; ta = tt; }
+        tmin = rmax(tmin, ta); tmax = rmin(tmax, tb);
+        if (tmax < tmin) return false;
+      }
+      t0 = tmin; t1 = tmax;
+      return true;
+    }
+  };
+  struct Node { Box bb; int l = -1, r = -1; size_t lo = 0, hi = 0; };
+  std::vector<int> prim_order;     // primitive ids in leaf order; id < tris.size(): triangle, else sphere id - tris.size()
+  std::vector<Node> nodes;
+  int bvh_root = -1;
+
+  Box prim_box(int id) const {
+    if (id < (int)tris.size()) { const Tri<R>& T = tris[id]; Box b(T.p1); b.expand(T.p2); b.expand(T.p3); return b; }
+    const Sph<R>& S = spheres[id - (int)tris.size()];
+    return Box(S.c - V(S.r, S.r, S.r), S.c + V(S.r, S.r, S.r));
+  }
+  int build_range(size_t l, size_t r, const Box& bbox, size_t max_leaf) {   // bvh.cpp:48-127
+    const size_t cnt = r - l;
+    const int me = (int)nodes.size();
+    nodes.push_back(Node()); nodes[me].bb = bbox;
+    if (cnt <= max_leaf) { nodes[me].lo = l; nodes[me].hi = r; return me; }
+    int axis;
+    if (bbox.ext[0] > bbox.ext[1] && bbox.ext[0] > bbox.ext[2]) axis = 0;
+    else if (bbox.ext[1] > bbox.ext[0] && bbox.ext[1] > bbox.ext[2]) axis = 1;
+    else axis = 2;
+    std::sort(prim_order.begin() + l, prim_order.begin() + r,
+              [&](int a, int b) { return prim_box(a).centroid()[axis] < prim_box(b).centroid()[axis]; });
+    std::vector<Box> right(cnt);
+    Box acc;
+    for (size_t i = r; i-- > l;) { acc.expand(prim_box(prim_order[i])); right[i - l] = acc; }
+    Box left = prim_box(prim_order[l]), lbest, rbest;
+    R best = Box::inf();
+    size_t split = l + 1;
+    for (size_t i = l + 1, nl = 1; i < r; i++, nl++) {
+      const R cost = left.area() * R((double)nl) + right[nl].area() * R((double)(cnt - nl));
+      if (cost < best) { best = cost; split = i; lbest = left; rbest = right[nl]; }
+      left.expand(prim_box(prim_order[i]));
+    }
+    const int lc = build_range(l, split, lbest, max_leaf);
+    const int rc = build_range(split, r, rbest, max_leaf);
+    nodes[me].l = lc; nodes[me].r = rc;
+    return me;
+  }
+  void build_bvh() {   // bvh.cpp:130-139, default max_leaf_size 4 (bvh.h:71)
+    nodes.clear(); prim_order.clear();
+    const int np = (int)(tris.size() + spheres.size());
+    Box all;
+    for (int i = 0; i < np; i++) { prim_order.push_back(i); all.expand(prim_box(i)); }
+    bvh_root = build_range(0, (size_t)np, all, 4);
+  }
+  bool prim_hit(int id, const V& o, const V& d, R& max_t, V* nrm) const {
+    return id < (int)tris.size() ? tri_hit(tris[id], o, d, max_t, nrm)
+                                 : sphere_hit_literal(spheres[id - (int)tris.size()], o, d, max_t, nrm);
+  }
+  // nrm == nullptr: any hit (bvh.cpp:142-163, first primitive found wins and sets max_t);
+  // nrm != nullptr: nearest hit (bvh.cpp:165-192: every primitive the boxes let through, each hit shrinks max_t)
+  bool bvh_hit(int node, const V& o, const V& d, R& max_t, V* nrm) const {
+    const Node& N = nodes[node];
+    R t0, t1;
+    if (!N.bb.hit(o, d, t0, t1)) return false;
+    if (t1 < R(0) || t0 > max_t) return false;
+    if (N.l < 0) {
+      bool hit = false;
+      for (size_t i = N.lo; i < N.hi; i++)
+        if (prim_hit(prim_order[i], o, d, max_t, nrm)) { if (!nrm) return true; hit = true; }
+      return hit;
+    }
+    if (!nrm) return bvh_hit(N.l, o, d, max_t, nrm) || bvh_hit(N.r, o, d, max_t, nrm);
+    bool hit = bvh_hit(N.l, o, d, max_t, nrm);
+    hit |= bvh_hit(N.r, o, d, max_t, nrm);
     return hit;
+  }
+  bool scene_hit(const V& o, const V& d, R& max_t, V* nrm) const { return bvh_hit(bvh_root, o, d, max_t, nrm); }
+
+  void set_spheres(size_t count, const double* cxcyczr) {
+    spheres.clear();
+    for (size_t k = 0; k < count; k++) {
+      const R r = R(cxcyczr[4 * k + 3]);
+      spheres.push_back(Sph<R>{V(R(cxcyczr[4 * k]), R(cxcyczr[4 * k + 1]), R(cxcyczr[4 * k + 2])), r, r * r});
+    }
+    build_bvh();
   }
 
   // ---- analytic box walls with the fp32 contact rules ------------------------
@@ -176,6 +302,33 @@ struct Oracle {
         if (t < R(0)) t = R(0);
         if (t <= max_t) { max_t = t; hit = true; *axis = a; *side = s; }
       }
+    }
+    return hit;
+  }
+
+  // One-sided obstacle spheres, the sphere analogue of the wall rules above: a sphere blocks only motion INTO
+  // it (d . (o - c) < 0); the entry root is clamped to t >= 0 and an origin on or inside the surface is in
+  // contact now (t = 0); motion away from the centre is never blocked.  For an origin outside the sphere
+  // this is exactly sphere_hit_literal (both roots share the sign of -b), so in fp64 the two modes agree as
+  // long as no particle is inside a sphere.  `skip`: the sphere currently being slid on.
+  bool sphere_hit_onesided(const V& o, const V& d, R& max_t, int* which, V* nrm, int skip) const {
+    bool hit = false;
+    for (int k = 0; k < (int)spheres.size(); k++) {
+      if (k == skip) continue;
+      const Sph<R>& S = spheres[k];
+      V m = o - S.c;
+      R b = R(2) * dot(m, d);
+      if (!(b < R(0))) continue;
+      R c = dot(m, m) - S.r2, t;
+      if (c <= R(0)) t = R(0);
+      else {
+        R a = dot(d, d);
+        R delta = b * b - R(4) * a * c;
+        if (delta < R(0)) continue;
+        t = (-b - std::sqrt(delta)) / (R(2) * a);
+        if (t < R(0)) t = R(0);
+      }
+      if (t <= max_t) { max_t = t; *which = k; V nn = o + t * d - S.c; *nrm = nn.unit(); hit = true; }
     }
     return hit;
   }
@@ -213,19 +366,27 @@ struct Oracle {
       // sticky virtual planes: d>0 && pt>=0 (fp64 never has pt==0; fp32 does)
       if (d.z > R(0)) { R pt = (ZF - p.z) / d.z; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
       if (d.y > R(0)) { R pt = (YL - p.y) / d.y; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
-      R max_t = l; int axis = -1, side = 0;
+      R max_t = l; int axis = -1, side = 0, sph = -1; V sn;
       bool hit = box_hit(p, d, max_t, &axis, &side, -1, 0);
+      if (sphere_hit_onesided(p, d, max_t, &sph, &sn, -1)) hit = true;      // nearest of walls and spheres
       if (hit || virt) {
         p += (max_t - EPS_D) * d;
         if (respond && hit && !virt) {
-          // exact axis normal n = +-e_axis: dot(d,n) > -1  <=>  d is not exactly anti-normal
-          R dn = side ? -d[axis] : d[axis];
-          V tang = delta_p; tang[axis] = R(0);   // delta - dot(delta,n) n, exactly
+          R dn; V tang;
+          if (sph >= 0) {                                  // radial normal (sphere.cpp:69-70); slide as particles.cpp:118-124
+            dn = dot(d, sn);
+            tang = delta_p - dot(delta_p, sn) * sn;
+          } else {
+            // exact axis normal n = +-e_axis: dot(d,n) > -1  <=>  d is not exactly anti-normal
+            dn = side ? -d[axis] : d[axis];
+            tang = delta_p; tang[axis] = R(0);             // delta - dot(delta,n) n, exactly
+          }
           if (dn > R(-1) && tang.norm2() > R(0)) {
             V d2 = tang.unit();
             R mt = (total_l - max_t) * R(0.5);
-            int a2 = -1, s2 = 0;
-            box_hit(p, d2, mt, &a2, &s2, axis, side);
+            int a2 = -1, s2 = 0, k2 = -1; V n2;
+            box_hit(p, d2, mt, &a2, &s2, sph >= 0 ? -1 : axis, side);      // the surface being slid on is never re-tested
+            sphere_hit_onesided(p, d2, mt, &k2, &n2, sph);
             p += (mt - EPS_D) * d2;
           }
         }

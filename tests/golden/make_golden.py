@@ -10,6 +10,7 @@ Fixtures
   ref_<name>.npz          reference output for 20 steps of timeStep(): sha256[:16] of <f8[N,7] per step,
                           coordinate sums, directed pair counts, the "avg rho: a => b" lines the reference
                           prints, full state at steps 0/1/19 and the ordered neighbour CSR of step 0
+  ref_sphere_<name>.npz   same with the CBspheres obstacle spheres in the reference's BVH (harness --sphere)
   ref_jitter_<name>.npz   same for jittered pgen-style inputs (lattice + U(-0.001,0.001),
                           default_rng(1234)) — the inputs used for fp32-vs-fp64 tolerance checks
 """
@@ -29,11 +30,14 @@ STEPS = 20
 KEEP = (0, 1, 19)
 
 
-def run_reference(pos, vel, rho0, steps):
+def run_reference(pos, vel, rho0, steps, spheres=()):
     with tempfile.TemporaryDirectory() as td:
         scene = os.path.join(td, "scene.bin"); dump = os.path.join(td, "dump.bin")
         write_bin_scene(scene, pos, vel, rho0)
-        subprocess.run([ref_harness_path(), "--bin", scene, "--steps", str(steps), "--out", dump, "--quiet"], check=True)
+        cmd = [ref_harness_path(), "--bin", scene, "--steps", str(steps), "--out", dump, "--quiet"]
+        for sp in spheres:                      # StaticScene::Sphere primitives added to the reference's BVH
+            cmd += ["--sphere"] + [repr(float(x)) for x in sp]
+        subprocess.run(cmd, check=True)
         log = open(dump + ".log").read()
         return read_dump(dump), log
 
@@ -92,8 +96,32 @@ def jitter_scenes():
     }
 
 
+# the two r = 0.3 obstacle spheres of the CBspheres scenes (dae/sky/CBspheres_lambertian.dae:291-305,575-594;
+# the file is z-up: (x, y, z) -> (x, z, -y)), both resting on the floor
+CB_SPHERES = np.array([[-0.4, 0.3, -0.3, 0.3], [0.4, 0.3, 0.3, 0.3]])
+
+
+def sphere_scenes():
+    """name -> (pos, vel, rho0, spheres, steps, keep): obstacle-sphere collision."""
+    two, vel, rho0 = jitter_scenes()["two_blocks"]
+    # "sphere drop" (BASELINE config 2): spheres_p.xml-style blocks collapsing around the CBspheres spheres
+    # a block thrown straight down onto sphere 1: direct hits and slides from the second step on
+    ph, vh = lattice_block(8, 8, 8, origin=(-0.75, 0.65, -0.65), spacing=0.1, v0=(0.0, -3.0, 0.0), jitter=0.001, seed=21)
+    return {
+        "sphere_drop": (two, vel, rho0, CB_SPHERES, 40, (0, 1, 19, 20, 39)),
+        "sphere_hit": (ph, vh, 700.0, CB_SPHERES, 12, (0, 1, 2, 3, 4, 5, 11)),
+    }
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    for name, (pos, vel, rho0, sph, steps, keep) in sphere_scenes().items():
+        dump, log = run_reference(pos, vel, rho0, steps, sph)
+        np.savez_compressed(os.path.join(GOLDEN, f"ref_{name}.npz"), pos=pos, vel=vel, rho0=rho0, spheres=sph, **pack(dump, log, keep))
+        inside = [int((np.linalg.norm(dump[-1]["state"][:, 0:3] - c[:3], axis=1) < c[3]).sum()) for c in sph]
+        print("spheres", name, pos.shape[0], "pairs", [len(d["col"]) for d in dump][:6], "particles inside a sphere at the end:", inside)
+    if "--only-spheres" in sys.argv:
+        return
     for name in ("p", "spheres_p"):
         pos, vel, rho0 = load_xml_scene(os.path.join(REFERENCE, "particles", name + ".xml"))
         np.savez_compressed(os.path.join(GOLDEN, f"scene_{name}.npz"), pos=pos, vel=vel, rho0=rho0)

@@ -69,6 +69,7 @@ def oracle_lib():
         lib.oracle_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_default_params.argtypes = [C.POINTER(PbfParams)]
         lib.oracle_set_threads.argtypes = [C.c_int]
+        lib.oracle_set_spheres.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -116,6 +117,11 @@ class Oracle:
 
     def estimate_densities(self):
         self.lib.oracle_estimate_densities(self.h)
+
+    def set_spheres(self, spheres):
+        """Obstacle spheres, rows (cx, cy, cz, r) (reference: StaticScene::Sphere primitives in the BVH)."""
+        sp = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        self.lib.oracle_set_spheres(self.h, sp.shape[0], _ptr(sp))
 
     def step(self, steps=1):
         self.lib.oracle_step(self.h, steps)

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--dims", type=int, nargs=3, default=[96, 20, 20])
     ap.add_argument("--iterations", type=int, default=12)
     ap.add_argument("--same-gpu", action="store_true")
+    ap.add_argument("--spheres", action="store_true", help="obstacle spheres on the floor, one of them across a slab boundary")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -49,11 +50,18 @@ def main():
     box_max = (0.1 * nx + 0.4, 0.1 * ny + 2.0, 0.1 * nz + 0.3)
     prm = dict(rest_density=700.0, iterations=args.iterations, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
     pos, vel = scene(nx, ny, nz)
+    # obstacle spheres are global scene data: every rank sets the same list.  The first one sits on the slab
+    # boundary of a 2-rank run; particles that would start inside a sphere are left out of the block.
+    spheres = np.array([[0.05 * nx, 0.6, 0.05 * nz, 0.7], [0.025 * nx, 1.2, 0.03 * nz, 0.5]]) if args.spheres else np.zeros((0, 4))
+    for c in spheres:
+        keep = np.linalg.norm(pos - c[:3], axis=1) > c[3] + 0.02
+        pos, vel = pos[keep], vel[keep]
     n = pos.shape[0]
     # rank r starts with the r-th contiguous chunk of the x-outer lattice order (roughly its slab)
-    per = (nx // world) * ny * nz
+    per = n // world
     lo = rank * per; hi = n if rank == world - 1 else (rank + 1) * per
     s = slab.SlabSolver(api.default_params(**prm), rank, world, device=local)
+    s.set_obstacle_spheres(spheres)
     s.upload_local(pos[lo:hi], vel[lo:hi], id_offset=lo)
     s.step(args.steps); s.sync()
     P, V, R, I, d, c = s.gather_all()
@@ -61,6 +69,7 @@ def main():
     out = {"world": world, "n": int(n), "steps": args.steps, "bounds": list(s.bounds), "col_bounds": list(map(int, s.col_bounds))}
     if rank == 0:
         g = api.Solver(api.default_params(**prm), device=local)
+        g.set_obstacle_spheres(spheres)
         g.upload(pos, vel); g.step(args.steps)
         Pg, Vg, Rg = g.download()
         dg, cg = g.neighbor_digest()
@@ -72,6 +81,7 @@ def main():
             "max_dpos": float(np.abs(P - Pg).max()) if len(P) == len(Pg) else None,
             "avg_rho_slab": [a_first, a_final], "avg_rho_single": [a, b],
             "finite": bool(np.isfinite(P).all()),
+            "min_sphere_gap": float(min((np.linalg.norm(P - c[:3], axis=1).min() - c[3]) for c in spheres)) if len(spheres) else None,
         })
         print("SLAB_RESULT " + json.dumps(out), flush=True)
     if world > 1:

@@ -354,6 +354,83 @@ def test_density_field_vs_reference_and_oracle(name):
         assert np.array_equal(a, b)
 
 
+SPHERE_SCENES = ["sphere_drop", "sphere_hit"]
+
+
+def _sphere_scene(name):
+    ref = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    states = [("init", ref["pos"], ref["vel"])]
+    keep = sorted(int(k) for k in ref["keep"])
+    for s in keep:
+        st = ref[f"state_{s}"]
+        states.append((f"ref_step{s}", st[:, 0:3], st[:, 3:6]))
+    return float(ref["rho0"]), ref["spheres"], states, ref, keep
+
+
+@pytest.mark.parametrize("name", SPHERE_SCENES)
+def test_obstacle_spheres_predict_and_neighbors_bit_exact(name):
+    """SURVEY.md §8 f-1.  With the CBspheres obstacle spheres in the collision scene the predicted positions
+    (swept move, nearest hit of walls and spheres, one slide along the sphere's tangent) and the frozen neighbour
+    sets equal the fp32 oracle's exactly; the oracle's fp64 build is pinned bit-exactly to the unmodified
+    reference with the same spheres in its BVH (tests/test_oracle_golden.py)."""
+    rho0, spheres, states, ref, _ = _sphere_scene(name)
+    touched = 0
+    for label, pos, vel in states:
+        g = _gpu(rho0, iterations=0); g.set_obstacle_spheres(spheres); g.capture(True)
+        g.upload(pos, vel); g.step(1)
+        o = _oracle(rho0, 32, iterations=0); o.set_spheres(spheres); o.upload(pos, vel); o.step(1)
+        xg = g.array(ARRAY_XPRED); xo = o.array(ARRAY_XPRED)
+        assert np.array_equal(xg, xo), f"{name}/{label}: x* differs (max {np.abs(xg - xo).max():.3e})"
+        assert np.array_equal(g.neighbor_digest()[0], o.digest()[0]), f"{name}/{label}: neighbour digests differ"
+        # the spheres matter: without them some predicted positions end up elsewhere
+        g0 = _gpu(rho0, iterations=0); g0.capture(True); g0.upload(pos, vel); g0.step(1)
+        touched += int(np.any(g0.array(ARRAY_XPRED) != xg, axis=1).sum())
+    assert touched >= 20, touched
+
+
+@pytest.mark.parametrize("name", SPHERE_SCENES)
+def test_obstacle_spheres_whole_step_vs_oracle_and_reference(name):
+    """Whole steps (12 iterations, collide against walls + spheres every iteration), teacher-forced from the
+    unmodified reference's own states: GPU vs fp32 oracle, vs fp64 oracle and vs the reference's next state, same
+    percentile gates as the box-only scenes."""
+    rho0, spheres, states, ref, keep = _sphere_scene(name)
+    for k, (label, pos, vel) in enumerate(states):
+        g = _gpu(rho0); g.set_obstacle_spheres(spheres); g.upload(pos, vel); g.step(1)
+        Pg, Vg, Rg = g.download()
+        for prec in (32, 64):
+            o = _oracle(rho0, prec); o.set_spheres(spheres); o.upload(pos, vel); o.step(1)
+            Po, Vo, Ro = o.download()
+            assert np.array_equal(g.neighbor_digest()[0], o.digest()[0]), f"{name}/{label}: neighbour sets differ from the fp{prec} oracle"
+            _gate_whole_step(f"{name}/{label} vs fp{prec} oracle", Pg, Rg, Po, Ro, rho0)
+        if k >= 1 and keep[k - 1] + 1 in keep:          # the reference's own next state is in the fixture
+            nxt = ref[f"state_{keep[k - 1] + 1}"]
+            _gate_whole_step(f"{name}/{label} vs unmodified reference", Pg, Rg, nxt[:, 0:3], nxt[:, 6], rho0)
+
+
+def test_obstacle_spheres_keep_particles_out_and_api_errors():
+    """60 free-running steps of the sphere drop: no particle ends up inside a sphere (beyond fp32 rounding of the
+    surface), the fluid does reach the spheres, and bad sphere lists are loud errors."""
+    from fluid_b200 import api
+    rho0, spheres, states, ref, _ = _sphere_scene("sphere_drop")
+    g = _gpu(rho0); g.set_obstacle_spheres(spheres); g.upload(states[0][1], states[0][2])
+    closest = np.inf
+    for _ in range(6):
+        g.step(10)
+        P = g.download()[0]
+        for c in spheres:
+            dist = np.linalg.norm(P - c[:3], axis=1)
+            assert dist.min() >= c[3] - 2e-6, dist.min()
+            closest = min(closest, dist.min() - c[3])
+    assert closest <= 1e-3                                     # particles do rest against the spheres
+    g.set_obstacle_spheres(np.zeros((0, 4)))                   # removing them is allowed
+    g.step(1)
+    with pytest.raises(api.PbfError) as e:
+        g.set_obstacle_spheres(np.tile(spheres[0], (9, 1)))
+    assert e.value.code == api.PBF_ERR_CAPACITY
+    with pytest.raises(api.PbfError):
+        g.set_obstacle_spheres([[0.0, 0.3, 0.0, -0.1]])
+
+
 def test_graph_replay_equals_plain_launches(monkeypatch):
     """Launch-bound scenes replay the step as a CUDA graph (one per buffer parity, PBF_GRAPH): the state after
     7 steps, a re-upload and 3 more steps is bit-identical to plain launches, and launch_count() still counts

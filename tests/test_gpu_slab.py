@@ -47,6 +47,13 @@ def test_two_slabs_shared_gpu_gloo():
     _check(_run(2, ["--backend", "gloo", "--same-gpu", "--steps", "6"], 29611))
 
 
+def test_two_slabs_with_obstacle_spheres():
+    """Obstacle spheres are global scene data set on every rank; one straddles the slab boundary."""
+    res = _run(2, ["--backend", "gloo", "--same-gpu", "--steps", "6", "--spheres"], 29616)
+    _check(res)
+    assert -2e-6 <= res["min_sphere_gap"] <= 1e-3, res["min_sphere_gap"]     # particles rest on the spheres, none inside
+
+
 def test_three_slabs_shared_gpu_gloo():
     """Three ranks: the middle slab has neighbours on both sides."""
     _check(_run(3, ["--backend", "gloo", "--same-gpu", "--steps", "5", "--dims", "120", "16", "16"], 29612))

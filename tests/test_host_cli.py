@@ -61,6 +61,19 @@ def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
     # step 0 against the unmodified reference's output
     dx = np.linalg.norm(d[0]["state"][:, 0:3] - ref["state_0"][:, 0:3], axis=1)
     assert np.percentile(dx, 50) <= 1e-5 and np.percentile(dx, 99) <= 5e-3 and dx.max() <= 1e-1
+    # obstacle spheres through the host adapter (Particles::setObstacleSpheres) == the Python binding
+    sref = np.load(os.path.join(GOLDEN, "ref_sphere_hit.npz"))
+    _write_xml(xml, sref["pos"], sref["vel"], float(sref["rho0"]))
+    cmd = [exe, "-p", xml, "--steps", "3", "--dump", dump, "--quiet"]
+    for c in sref["spheres"]:
+        cmd += ["--sphere"] + [repr(float(v)) for v in c]
+    assert subprocess.run(cmd, capture_output=True, text=True).returncode == 0
+    d = read_dump(dump)
+    g = api.Solver(api.default_params(rest_density=float(sref["rho0"])))
+    g.set_obstacle_spheres(sref["spheres"]); g.upload(sref["pos"], sref["vel"]); g.estimate_densities(); g.step(3)
+    P, V, R = g.download()
+    assert np.array_equal(d[2]["state"][:, 0:3], P) and np.array_equal(d[2]["state"][:, 3:6], V)
+    _write_xml(xml, ref["pos"], ref["vel"], float(ref["rho0"]))
     # -d 0.05 => ceil(0.05/0.016) = 4 steps (while simulate_time < T, Q18)
     r = subprocess.run([exe, "-p", xml, "-d", "0.05", "--quiet"], capture_output=True, text=True)
     assert json.loads(r.stderr.strip().splitlines()[-1])["steps"] == 4

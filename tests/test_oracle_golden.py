@@ -14,6 +14,7 @@ from helpers import (COLLIDE_BOX, COLLIDE_TRIANGLES, GOLDEN, SEARCH_BRUTE, SEARC
 
 SHIPPED = ["p", "spheres_p"]
 JITTER = ["two_blocks", "sparse", "corner", "front"]
+SPHERES = ["sphere_drop", "sphere_hit"]     # the CBspheres obstacle spheres in the reference's BVH
 
 
 def _load(name):
@@ -21,8 +22,15 @@ def _load(name):
         sc = np.load(os.path.join(GOLDEN, f"scene_{name}.npz"))
         ref = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
         return sc["pos"], sc["vel"], float(sc["rho0"]), ref
-    ref = np.load(os.path.join(GOLDEN, f"ref_jitter_{name}.npz"))
+    ref = np.load(os.path.join(GOLDEN, f"ref_{name}.npz" if name in SPHERES else f"ref_jitter_{name}.npz"))
     return ref["pos"], ref["vel"], float(ref["rho0"]), ref
+
+
+def _oracle(rho0, ref, cmode, search=SEARCH_GRID, xsph=XSPH_REFERENCE):
+    o = Oracle(default_params(rest_density=rho0, xsph_mode=xsph), 64, cmode, search)
+    if "spheres" in ref.files:
+        o.set_spheres(ref["spheres"])
+    return o
 
 
 def test_constants():
@@ -35,12 +43,14 @@ def test_constants():
     assert abs(1.0 / w - 0.017761411379071678) < 1e-15
 
 
-@pytest.mark.parametrize("name", SHIPPED + JITTER)
+@pytest.mark.parametrize("name", SHIPPED + JITTER + SPHERES)
 @pytest.mark.parametrize("search", [SEARCH_BRUTE, SEARCH_GRID])
 def test_oracle_matches_reference_fixture(name, search):
+    """With obstacle spheres the oracle walks a restatement of the reference's own BVH (bvh.cpp:48-192), because
+    clamp() takes the first primitive the traversal finds, not the nearest (particles.cpp:76)."""
     pos, vel, rho0, ref = _load(name)
     steps = len(ref["sha"])
-    o = Oracle(default_params(rest_density=rho0, xsph_mode=XSPH_REFERENCE), 64, COLLIDE_TRIANGLES, search)
+    o = _oracle(rho0, ref, COLLIDE_TRIANGLES, search)
     o.upload(pos, vel); o.estimate_densities()
     keep = set(int(k) for k in ref["keep"])
     for s in range(steps):
@@ -73,29 +83,37 @@ def test_survey_golden_values():
     assert [int(ref["pairs"][s]) for s in (0, 1, 19)] == [157750, 125400, 153134]
 
 
-@pytest.mark.parametrize("name", SHIPPED + JITTER)
+@pytest.mark.parametrize("name", SHIPPED + JITTER + SPHERES)
 def test_analytic_box_equals_triangles_fp64(name):
     """Chain of trust, second arrow: the analytic box with the fp32 contact rules (one-sided planes,
     exact axis normals, sticky virtual planes) is the same operator as the
     reference's triangle walls in fp64.  Teacher-forced per step from the reference's own state:
     neighbour lists identical, state equal up to the rounding of the hit distance t
-    (Moller-Trumbore vs (plane-o)/d: a few ulp, amplified by at most the 12 iterations)."""
+    (Moller-Trumbore vs (plane-o)/d: a few ulp, amplified by at most the 12 iterations).
+    Obstacle spheres: the one-sided sphere rule (blocks only motion into the sphere, entry root clamped to
+    t >= 0, nearest hit) against the reference's Sphere::test + BVH any-hit order."""
     pos, vel, rho0, ref = _load(name)
     keep = sorted(int(k) for k in ref["keep"])
-    prm = default_params(rest_density=rho0, xsph_mode=XSPH_REFERENCE)
+    checked = 0
     for k, s in enumerate(keep[:-1]):
         if keep[k + 1] != s + 1:
             continue
         st = ref[f"state_{s}"]; nxt = ref[f"state_{s + 1}"]
         res = []
         for cm in (COLLIDE_TRIANGLES, COLLIDE_BOX):
-            o = Oracle(prm, 64, cm, SEARCH_GRID)
+            o = _oracle(rho0, ref, cm)
             o.upload(st[:, 0:3], st[:, 3:6]); o.step()
             res.append(o.download() + (o.neighbors(),))
         assert np.array_equal(res[0][0], nxt[:, 0:3])              # triangles == reference (teacher-forced)
         assert np.array_equal(res[0][3][1], res[1][3][1])           # identical ordered neighbour lists
         assert np.abs(res[0][0] - res[1][0]).max() < 1e-11
         assert np.abs(res[0][2] - res[1][2]).max() < 1e-8 * rho0
+        checked += 1
+    assert checked >= 1
+    if name in SPHERES:     # the fixture really exercises sphere contacts: particles within 1e-6 of a sphere surface
+        P = ref[f"state_{keep[-1]}"][:, 0:3]
+        near = sum(int((np.abs(np.linalg.norm(P - c[:3], axis=1) - c[3]) < 1e-6).sum()) for c in ref["spheres"])
+        assert near >= 10, near
 
 
 @pytest.mark.parametrize("name", SHIPPED)
