@@ -96,6 +96,7 @@ void Particles::timeStep(double delta_t) {
   pbf_stats(handle_, &avg_rho_first_iter, &avg_rho_final, &ms);
   if (!quiet) std::cout << "avg rho: " << avg_rho_first_iter << " => " << avg_rho_final << std::endl;   // particles.cpp:267,279,295
   surfaceUpToTimestep = false;                                   // particles.cpp:296
+  steps_taken++;
 }
 
 void Particles::timeStep() { timeStep(params_.dt); }             // DEFAULT_DELTA_T, particles.cpp:299-301
@@ -120,6 +121,51 @@ std::vector<double> Particles::estimateDensitiesAt(const std::vector<Vector3D>& 
   for (size_t i = 0; i < points.size(); i++) { q[3*i] = points[i].x; q[3*i+1] = points[i].y; q[3*i+2] = points[i].z; }
   if (pbf_density_at(handle_, points.size(), q.data(), out.data()) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   return out;
+}
+
+// ---- restart files ------------------------------------------------------------------------------
+bool Particles::saveCheckpoint(const char* filename, std::string* error) const {
+  FILE* f = fopen(filename, "wb");
+  if (!f) { if (error) *error = std::string("cannot open ") + filename; return false; }
+  const int64_t n = (int64_t)ps.size(), steps = steps_taken, psz = (int64_t)sizeof(PbfParams), ns = (int64_t)(spheres_.size() / 4);
+  std::vector<double> buf(7 * (size_t)n);
+  for (int64_t i = 0; i < n; i++) {                // from the host mirror: exactly the fp32 device state, widened
+    const Particle* p = ps[i];
+    buf[3*i] = p->position.x; buf[3*i+1] = p->position.y; buf[3*i+2] = p->position.z;
+    buf[3*n + 3*i] = p->velocity.x; buf[3*n + 3*i+1] = p->velocity.y; buf[3*n + 3*i+2] = p->velocity.z;
+    buf[6*n + i] = p->density;
+  }
+  bool ok = fwrite("PBFCKPT1", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&steps, 8, 1, f) == 1 &&
+            fwrite(&simulate_time, 8, 1, f) == 1 && fwrite(&rest_density, 8, 1, f) == 1 && fwrite(&psz, 8, 1, f) == 1 &&
+            fwrite(&params_, sizeof(PbfParams), 1, f) == 1 && fwrite(&ns, 8, 1, f) == 1 &&
+            (ns == 0 || fwrite(spheres_.data(), 8, spheres_.size(), f) == spheres_.size()) &&
+            (n == 0 || fwrite(buf.data(), 8, buf.size(), f) == buf.size());
+  ok = (fclose(f) == 0) && ok;
+  if (!ok && error) *error = std::string("short write to ") + filename;
+  return ok;
+}
+
+Particles* Particles::loadCheckpoint(const char* filename, std::string* error, int device) {
+  auto fail = [&](const std::string& m) -> Particles* { if (error) *error = m; return nullptr; };
+  FILE* f = fopen(filename, "rb");
+  if (!f) return fail(std::string("cannot open ") + filename);
+  char magic[8]; int64_t n = 0, steps = 0, psz = 0, ns = 0; double t = 0, rho0 = 0; PbfParams prm;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "PBFCKPT1", 8) == 0 && fread(&n, 8, 1, f) == 1 && fread(&steps, 8, 1, f) == 1 &&
+            fread(&t, 8, 1, f) == 1 && fread(&rho0, 8, 1, f) == 1 && fread(&psz, 8, 1, f) == 1 && psz == (int64_t)sizeof(PbfParams) &&
+            fread(&prm, sizeof(PbfParams), 1, f) == 1 && fread(&ns, 8, 1, f) == 1 && n >= 0 && ns >= 0 && ns <= PBF_MAX_SPHERES;
+  if (!ok) { fclose(f); return fail("not a PBFCKPT1 checkpoint (or written with another PbfParams layout)"); }
+  std::vector<double> sph(4 * (size_t)ns), buf(7 * (size_t)n);
+  ok = (ns == 0 || fread(sph.data(), 8, sph.size(), f) == sph.size()) && (n == 0 || fread(buf.data(), 8, buf.size(), f) == buf.size());
+  fclose(f);
+  if (!ok) return fail("truncated checkpoint");
+  Particles* ps = new Particles(rho0, &prm, device);
+  for (int64_t i = 0; i < n; i++) {
+    ps->addParticle(Vector3D(buf[3*i], buf[3*i+1], buf[3*i+2]), Vector3D(buf[3*n + 3*i], buf[3*n + 3*i+1], buf[3*n + 3*i+2]));
+    ps->ps.back()->density = buf[6*n + i];
+  }
+  ps->simulate_time = t; ps->steps_taken = steps;
+  if (ns) ps->setObstacleSpheres(sph);
+  return ps;
 }
 
 std::string Particles::paramsString() const {

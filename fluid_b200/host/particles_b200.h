@@ -66,6 +66,14 @@ struct Particles {
   double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
   // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
   std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);
+  // Restart file: magic "PBFCKPT1", int64 n, int64 steps, double simulate_time, double rho0,
+  // int64 sizeof(PbfParams) + the struct, int64 number of obstacle spheres + rows, then pos[3n], vel[3n],
+  // density[n] as little-endian doubles in original particle order.  The device state is fp32 and its layout is
+  // a pure function of (positions, velocities, ids), so a run continued from a checkpoint is bit-identical to
+  // the uninterrupted run.
+  bool saveCheckpoint(const char* filename, std::string* error = nullptr) const;
+  static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0);   // nullptr on error
+  long long steps_taken = 0;
   std::string paramsString() const;              // particles.cpp:420-438
   // the two numbers of the reference's "avg rho: a => b" line for the last step
   double avg_rho_first_iter = 0.0, avg_rho_final = 0.0;
@@ -86,6 +94,7 @@ struct Particles {
 // <particle><pos>x y z</pos><v>x y z</v></particle>...  Density goes through float like stof (Q17).
 // Streaming reader (no DOM), so multi-million-particle files are fine.  Returns nullptr on error.
 Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0);
+inline Particles* load_checkpoint(const char* filename, std::string* error = nullptr, int device = 0) { return Particles::loadCheckpoint(filename, error, device); }
 // parse only: positions / velocities (AoS doubles) and rho0; false on error
 bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::vector<double>& vel, double& rho0, std::string* error);
 

@@ -4,6 +4,7 @@
 // Optional --dump writes the per-step state in the same PBFDUMP1 format as oracle/ref_harness.
 //   pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--iterations I]
 //           [--sphere cx cy cz r]...      obstacle spheres of the collision scene (the CBspheres scenes hold two)
+//           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -17,7 +18,7 @@
 using namespace pbfhost;
 
 int main(int argc, char** argv) {
-  const char* pfile = nullptr; const char* dump = nullptr;
+  const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
   std::vector<double> spheres;
   for (int i = 1; i < argc; i++) {
@@ -28,11 +29,13 @@ int main(int argc, char** argv) {
     else if (a == "--iterations" && i + 1 < argc) iterations = atoi(argv[++i]);
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
     else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }   // obstacle sphere cx cy cz r, repeatable
+    else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
+    else if (a == "--load-state" && i + 1 < argc) load_state = argv[++i];   // continue from a restart file instead of -p
     else if (a == "--quiet") quiet = true;
     else if (a == "--parse-only") parse_only = true;
     else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--sphere cx cy cz r]...\n"); return 2; }
   }
-  if (!pfile) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
+  if (!pfile && !load_state) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
   std::string err;
   if (parse_only) {
     std::vector<double> pos, vel; double rho0 = 0;
@@ -46,8 +49,8 @@ int main(int argc, char** argv) {
   PbfParams prm; pbf_default_params(&prm);
   if (iterations >= 0) prm.iterations = iterations;
   printf("[Fluid Simulation] Loading particle file...");
-  Particles* ps = load_particles_xml(pfile, &err, &prm, 0);
-  if (!ps) { printf("[ERROR] XML error: %s\n", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
+  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0) : load_particles_xml(pfile, &err, &prm, 0);
+  if (!ps) { printf("[ERROR] %s: %s\n", load_state ? "checkpoint error" : "XML error", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
   printf("Done!\n");
   ps->quiet = quiet;
   if (!spheres.empty()) ps->setObstacleSpheres(spheres);
@@ -82,6 +85,7 @@ int main(int argc, char** argv) {
     for (auto& st : frames) { fwrite(st.data(), 8, st.size(), f); fwrite(zero.data(), 4, n, f); fwrite(&per, 8, 1, f); }
     fclose(f);
   }
+  if (save_state && !ps->saveCheckpoint(save_state, &err)) { printf("[ERROR] %s\n", err.c_str()); return EXIT_FAILURE; }
   fprintf(stderr, "{\"n\": %lld, \"steps\": %d, \"seconds_total\": %.6f, \"ms_per_step_incl_readback\": %.4f}\n", (long long)n, done, secs,
           done ? 1e3 * secs / done : 0.0);
   delete ps;

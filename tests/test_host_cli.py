@@ -73,6 +73,20 @@ def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
     g.set_obstacle_spheres(sref["spheres"]); g.upload(sref["pos"], sref["vel"]); g.estimate_densities(); g.step(3)
     P, V, R = g.download()
     assert np.array_equal(d[2]["state"][:, 0:3], P) and np.array_equal(d[2]["state"][:, 3:6], V)
+    # restart files: 2 steps + checkpoint + 2 more steps == 4 uninterrupted steps, bit for bit (spheres travel along)
+    ck = str(tmp_path / "state.ckpt"); dump2 = str(tmp_path / "d2.bin")
+    base = [exe, "--quiet"]
+    sph = cmd[cmd.index("--sphere"):]
+    assert subprocess.run(base + ["-p", xml, "--steps", "4", "--dump", dump] + sph, capture_output=True).returncode == 0
+    assert subprocess.run(base + ["-p", xml, "--steps", "2", "--save-state", ck] + sph, capture_output=True).returncode == 0
+    assert open(ck, "rb").read(8) == b"PBFCKPT1"
+    r = subprocess.run(base + ["--load-state", ck, "--steps", "2", "--dump", dump2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d4, d22 = read_dump(dump), read_dump(dump2)
+    assert np.array_equal(d4[3]["state"][:, :7], d22[1]["state"][:, :7])
+    open(ck, "r+b").write(b"NOTACKPT")
+    r = subprocess.run(base + ["--load-state", ck, "--steps", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "checkpoint error" in r.stdout
     _write_xml(xml, ref["pos"], ref["vel"], float(ref["rho0"]))
     # -d 0.05 => ceil(0.05/0.016) = 4 steps (while simulate_time < T, Q18)
     r = subprocess.run([exe, "-p", xml, "-d", "0.05", "--quiet"], capture_output=True, text=True)
