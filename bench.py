@@ -265,8 +265,7 @@ def main():
 
     # per-kernel table from CUDA events recorded on the launching stream during the timed region
     kernels = {}
-    # solve_fused = all I iterations (lambda + delta-p) in one cooperative launch
-    alg = {"lambda": BYTES_LAMBDA, "delta_collide": BYTES_DELTA, "solve_fused": (BYTES_LAMBDA + BYTES_DELTA) * iters}
+    alg = {"lambda": BYTES_LAMBDA, "delta_collide": BYTES_DELTA}
     for name, (ms, cnt) in prof.items():
         if cnt:
             e = {"launches": cnt, "ms_per_launch": ms / cnt, "share": ms / max(dev_ms, 1e-9)}

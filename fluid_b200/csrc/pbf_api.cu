@@ -70,7 +70,8 @@ namespace {
 
 void free_arrays(pbf_handle* h) {
   for (int b = 0; b < 2; b++) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); cudaFree(h->orig[b]); h->pos[b] = h->vel[b] = nullptr; h->orig[b] = nullptr; }
-  cudaFree(h->xs_tmp); cudaFree(h->xs_a); cudaFree(h->xs_b); cudaFree(h->vtmp); cudaFree(h->omega); cudaFree(h->xpred);
+  cudaFree(h->xs_tmp); cudaFree(h->xs_a); cudaFree(h->xs_b); cudaFree(h->vtmp); cudaFree(h->omega); cudaFree(h->xpred); cudaFree(h->xv);
+  h->xv = nullptr;
   cudaFree(h->rho); cudaFree(h->cell_of); cudaFree(h->rank); cudaFree(h->perm); cudaFree(h->key);
   cudaFree(h->nbr); cudaFree(h->slice_off); cudaFree(h->nbr_cnt); cudaFree(h->io_stage);
   h->xs_tmp = h->xs_a = h->xs_b = h->vtmp = h->omega = h->xpred = nullptr; h->rho = nullptr;
@@ -89,7 +90,7 @@ int pbf::alloc_particle_arrays(Solver* hs, size_t n) {
   const size_t cap = (n + 1 + 31) / 32 * 32 + 32;
   for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
   CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
-  CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap));
+  CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap)); CK(h, dmalloc(&h->xv, 2 * cap));
   CK(h, dmalloc(&h->cell_of, cap)); CK(h, dmalloc(&h->rank, cap)); CK(h, dmalloc(&h->perm, cap)); CK(h, dmalloc(&h->key, cap));
   CK(h, dmalloc(&h->slice_off, cap / 32 + 1)); CK(h, dmalloc(&h->nbr_cnt, cap));
   CK(h, dmalloc(&h->io_stage, cap * 7));
@@ -181,17 +182,10 @@ struct HandleExtra {
     return e;
   }
 };
-static HandleExtra* extra_of(pbf_handle* h);
-
-#include <map>
-#include <mutex>
-static std::map<pbf_handle*, HandleExtra*> g_extra;
-static std::mutex g_extra_mu;
+// owned by the handle (Solver::host_extra), created on first use, freed in pbf_destroy: no global state
 static HandleExtra* extra_of(pbf_handle* h) {
-  std::lock_guard<std::mutex> g(g_extra_mu);
-  auto it = g_extra.find(h);
-  if (it != g_extra.end()) return it->second;
-  return g_extra[h] = new HandleExtra();
+  if (!h->host_extra) h->host_extra = new HandleExtra();
+  return static_cast<HandleExtra*>(h->host_extra);
 }
 
 extern "C" {
@@ -253,11 +247,7 @@ void pbf_destroy(pbf_handle* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); for (int k = 0; k < 4; k++) if (h->ev_rb[k]) cudaEventDestroy(h->ev_rb[k]); }
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
-  {
-    std::lock_guard<std::mutex> g(g_extra_mu);
-    auto it = g_extra.find(h);
-    if (it != g_extra.end()) { delete it->second; g_extra.erase(it); }
-  }
+  delete static_cast<HandleExtra*>(h->host_extra);
   delete h;
 }
 

@@ -112,6 +112,9 @@ __device__ __forceinline__ bool ex_sphere_hit(const DevParams& P, float3 o, floa
 // clamp_response() (respond=true: slide once along the wall, particles.cpp:87-132), with the
 // fp32 contact rules of SURVEY.md §7.3-4 (one-sided planes, exact axis normals, sticky virtual
 // planes).  Mirrors Oracle<float>::collide(COLLIDE_ANALYTIC_BOX) operation for operation.
+// SPH: obstacle spheres compiled in (the kernels are instantiated both ways and the box-only build is launched when
+// the scene has no spheres, so box-only scenes pay nothing for them).
+template <bool SPH>
 __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float3 delta, bool respond) {
   const float total_l = __fsqrt_rn(ex_norm2(delta.x, delta.y, delta.z));
   float l = total_l;
@@ -124,7 +127,7 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
     float max_t = l; int axis = -1, side = 0, sph = -1;
     float3 sn = make_float3(0.f, 0.f, 0.f);
     bool hit = ex_box_hit(P, p, d, max_t, axis, side, -1, 0);
-    if (P.n_sph > 0 && ex_sphere_hit(P, p, d, max_t, sph, sn, -1)) hit = true;   // nearest of walls and spheres
+    if (SPH && ex_sphere_hit(P, p, d, max_t, sph, sn, -1)) hit = true;           // nearest of walls and spheres
     if (hit || virt) {
       const float s = __fsub_rn(max_t, P.eps_d);
       p.x = __fadd_rn(p.x, __fmul_rn(s, d.x));
@@ -132,7 +135,7 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
       p.z = __fadd_rn(p.z, __fmul_rn(s, d.z));
       if (respond && hit && !virt) {
         float dn; float3 tg = delta;
-        if (sph >= 0) {                                  // radial normal; tangent = delta - (delta . n) n
+        if (SPH && sph >= 0) {                           // radial normal; tangent = delta - (delta . n) n
           dn = ex_dot(d, sn);
           const float dd = ex_dot(delta, sn);
           tg = make_float3(__fsub_rn(delta.x, __fmul_rn(dd, sn.x)), __fsub_rn(delta.y, __fmul_rn(dd, sn.y)), __fsub_rn(delta.z, __fmul_rn(dd, sn.z)));
@@ -146,8 +149,8 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
           float3 d2 = make_float3(__fmul_rn(rn, tg.x), __fmul_rn(rn, tg.y), __fmul_rn(rn, tg.z));
           float mt = __fmul_rn(__fsub_rn(total_l, max_t), 0.5f);
           int a2 = -1, s2 = 0, k2 = -1; float3 n2;
-          ex_box_hit(P, p, d2, mt, a2, s2, sph >= 0 ? -1 : axis, side);     // the surface being slid on is never re-tested
-          if (P.n_sph > 0) ex_sphere_hit(P, p, d2, mt, k2, n2, sph);
+          ex_box_hit(P, p, d2, mt, a2, s2, (SPH && sph >= 0) ? -1 : axis, side);   // the surface being slid on is never re-tested
+          if (SPH) ex_sphere_hit(P, p, d2, mt, k2, n2, sph);
           const float s3 = __fsub_rn(mt, P.eps_d);
           p.x = __fadd_rn(p.x, __fmul_rn(s3, d2.x));
           p.y = __fadd_rn(p.y, __fmul_rn(s3, d2.y));

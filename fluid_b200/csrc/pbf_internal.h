@@ -23,10 +23,10 @@ struct Scalars {
 };
 
 enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
-                K_VELOCITY, K_VORT_XSPH, K_CONFINE, K_DENSITY, K_IO, K_SLAB, K_SOLVE_FUSED, K_COUNT };
+                K_VELOCITY, K_VORT_XSPH, K_CONFINE, K_DENSITY, K_IO, K_SLAB, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {
   "predict_collide_hash", "cell_scan", "scatter", "cell_sort", "reorder", "build_neighbors", "lambda",
-  "delta_collide", "velocity", "vorticity_xsph", "confine_commit", "density_only", "io", "slab", "solve_fused"};
+  "delta_collide", "velocity", "vorticity_xsph", "confine_commit", "density_only", "io", "slab"};
 
 struct Solver {
   int device = 0;
@@ -41,6 +41,7 @@ struct Solver {
   float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
   uint32_t* orig[2] = {nullptr, nullptr};
   float4 *xs_tmp = nullptr, *xs_a = nullptr, *xs_b = nullptr, *vtmp = nullptr, *omega = nullptr, *xpred = nullptr;
+  float4* xv = nullptr;              // 2 float4 per particle: (x*, v) record gathered by the vorticity/XSPH pass
   float* rho = nullptr;
   uint32_t *cell_of = nullptr, *rank = nullptr, *perm = nullptr, *key = nullptr;
   uint32_t *cell_count = nullptr, *cell_start = nullptr, *block_sums = nullptr;
@@ -60,9 +61,8 @@ struct Solver {
   size_t n_in_cap() const { return slab ? cap : 0; }
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
+  void* host_extra = nullptr;        // pbf_api.cu's HandleExtra (pinned staging, registered host ranges)
   int capture_xpred = 0;
-  int fused_state = 0;               // 0 unknown, 1 cooperative fused iterations available, -1 not
-  unsigned fused_grid = 0;
   bool have_neighbors = false;
   long long rebinned_at = -1;
   // streaming read-back (pbf_set_readback): results leave for page-locked host buffers as soon as each is final
@@ -120,7 +120,6 @@ void enqueue_estimate_densities(Solver* h);
 void enqueue_predict_hash(Solver* h, int apply_forces);
 void enqueue_sort(Solver* h, size_t n_in);
 void enqueue_build(Solver* h, int include_self);
-bool enqueue_solve_fused(Solver* h);
 enum { PART_ALL = 0, PART_BOUNDARY = 1, PART_INTERIOR = 2 };
 void enqueue_lambda(Solver* h, int first_iter, int part);
 void enqueue_delta(Solver* h, int part);

@@ -6,8 +6,6 @@
 //   the predicted positions, like the reference's all-pairs loop 258-265) -> I x (lambda, delta-p +
 //   collide) -> velocity, vorticity + XSPH + density -> confinement + commit.
 // No tensor cores: this is a gather-bound stencil, not a contraction.
-#include <cooperative_groups.h>
-
 #include "pbf_internal.h"
 
 namespace pbf {
@@ -27,6 +25,7 @@ __device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x,
 // emigrant: it is packed (3 float4: x with the global id in .w, x*, v) into the message for the
 // x-neighbour and dropped from the local sort (cell_of stays INVALID).  Single-GPU mode owns every
 // column, so nothing ever emigrates.
+template <bool SPH>
 __global__ void __launch_bounds__(TPB)
 k_predict_hash(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ pos,
                float4* __restrict__ vel, const uint32_t* __restrict__ orig, float4* __restrict__ xs_tmp,
@@ -45,7 +44,7 @@ k_predict_hash(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, con
   if (apply_forces) {
     v.y = __fsub_rn(v.y, P.gdt);                                   // velocity.y -= 10 * delta_t
     const float3 delta = make_float3(__fmul_rn(v.x, P.dt), __fmul_rn(v.y, P.dt), __fmul_rn(v.z, P.dt));
-    p = ex_collide(P, p, delta, true);
+    p = ex_collide<SPH>(P, p, delta, true);
     vel[i] = v;                                                    // clamp_response leaves v untouched (Q9)
   }
   if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { atomicOr(&sc->err, ERRBIT_NONFINITE); p = make_float3(P.clo[0], P.clo[1], P.clo[2]); }
@@ -150,12 +149,42 @@ k_scatter(uint32_t n, const uint32_t* __restrict__ cell_of, const uint32_t* __re
 // by their original id makes the whole layout (and therefore every floating-point sum downstream)
 // a pure function of the particle state: runs are bit-reproducible, and a slab decomposition sees
 // the same order as one GPU does.
-__global__ void __launch_bounds__(TPB)
+// One thread per cell.  Up to 32 particles (a lattice at spacing h/3 has 27 per cell): the (id, slot) pairs are
+// loaded into registers as 64-bit words and sorted by a fully unrolled 32-input bitonic network (240 compare-
+// exchanges, compile-time indices, no memory traffic); unused inputs hold +inf.  Fuller cells fall back to an
+// insertion sort in global memory.
+__global__ void __launch_bounds__(128)
 k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ perm,
             uint32_t* __restrict__ key) {
-  const uint32_t c = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t c = blockIdx.x * 128 + threadIdx.x;
   if (c >= ncell) return;
   const uint32_t s = cell_start[c], e = cell_start[c + 1];
+  const uint32_t cnt = e - s;
+  if (cnt <= 1u) return;
+  if (cnt <= 32u) {
+    unsigned long long v[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++)
+      v[k] = (uint32_t)k < cnt ? ((unsigned long long)key[s + k] << 32) | perm[s + k] : ~0ull;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const int l = i ^ j;
+          if (l > i) {
+            const bool up = (i & k) == 0;
+            const unsigned long long a = v[i], b = v[l];
+            const bool sw = (a > b) == up;
+            v[i] = sw ? b : a; v[l] = sw ? a : b;
+          }
+        }
+#pragma unroll
+    for (int k = 0; k < 32; k++)
+      if ((uint32_t)k < cnt) { key[s + k] = (uint32_t)(v[k] >> 32); perm[s + k] = (uint32_t)v[k]; }
+    return;
+  }
   for (uint32_t a = s + 1; a < e; a++) {
     const uint32_t k = key[a], p = perm[a];
     uint32_t b = a;
@@ -239,7 +268,7 @@ __device__ __forceinline__ void nb_run_range(const DevParams& P, const uint32_t*
   e = cell_start[base + zhi + 1];
 }
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 5)      // 48 registers: 5 CTAs per SM (50 would round up to 56 and lose one)
 k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt_range, uint32_t sentinel,
                   const float4* __restrict__ xs,
                   const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ nbr,
@@ -313,8 +342,10 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
 }
 
 // the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
-__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega) {
+__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega, float4* xv) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    xv[2 * (size_t)n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    xv[2 * (size_t)n + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     a[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     b[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     w[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
@@ -350,12 +381,6 @@ __device__ __forceinline__ float block_sum_to_double(float v, double* target) {
   return v;
 }
 
-// NC = true: neighbour data comes through the read-only path (__ldg); the standalone kernels use it.
-// The fused cooperative kernel writes the same arrays earlier in the same launch, so it must use
-// ordinary (coherent after grid.sync) loads: NC = false.
-template <bool NC> __device__ __forceinline__ float4 ld4(const float4* p) { return NC ? __ldg(p) : *p; }
-
-template <bool NC>
 __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t, uint32_t i, const float4* __restrict__ xs_in,
                                                  float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr,
                                                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
@@ -364,7 +389,7 @@ __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t,
   float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
 #define BODY_L(J)                                                          \
   {                                                                        \
-    const float4 pj = ld4<NC>(&xs_in[J]);                                  \
+    const float4 pj = __ldg(&xs_in[J]);                                  \
     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;      \
     float r2, w3, g;                                                       \
     pair_terms(P, dx, dy, dz, r2, w3, g);                                  \
@@ -392,7 +417,7 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multip
          const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
   const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
   float rho = 0.f;
-  if (t < n) rho = lambda_particle<true>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out);
+  if (t < n) rho = lambda_particle(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out);
   if (rho_sum) block_sum_to_double(rho, rho_sum);
 }
 
@@ -401,7 +426,7 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multip
 //    reads xs_in = (x*, lambda), writes xs_out.xyz = corrected position
 //    NCORR: artificial-pressure exponent known at compile time (4 = reference), or -1 = runtime.
 // ------------------------------------------------------------------------------------------------
-template <int NCORR, bool NC>
+template <int NCORR, bool SPH>
 __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, uint32_t i, const float4* __restrict__ xs_in,
                                                float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr,
                                                const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt) {
@@ -409,7 +434,7 @@ __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, u
   float ax = 0.f, ay = 0.f, az = 0.f;
 #define BODY_D(J)                                                          \
   {                                                                        \
-    const float4 pj = ld4<NC>(&xs_in[J]);                                  \
+    const float4 pj = __ldg(&xs_in[J]);                                  \
     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;      \
     float r2, w3, g;                                                       \
     pair_terms(P, dx, dy, dz, r2, w3, g);                                  \
@@ -424,60 +449,49 @@ __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, u
 #undef BODY_D
   const float sc = P.spiky_c * P.inv_rho0;
   const float3 dp = make_float3(sc * ax, sc * ay, sc * az);
-  const float3 p = ex_collide(P, make_float3(pi.x, pi.y, pi.z), dp, false);
+  const float3 p = ex_collide<SPH>(P, make_float3(pi.x, pi.y, pi.z), dp, false);
   xs_out[i] = make_float4(p.x, p.y, p.z, 0.f);
 }
 
-template <int NCORR>
+template <int NCORR, bool SPH>
 __global__ void __launch_bounds__(TPB)
 k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
         const uint32_t* __restrict__ nbr_cnt) {
   const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
   if (t >= n) return;
-  delta_particle<NCORR, true>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt);
-}
-
-// All solver iterations in ONE cooperative launch: a persistent grid (every CTA resident) walks the
-// particles grid-stride through lambda pass / grid.sync / delta-p pass / grid.sync, I times.  The
-// stride is a multiple of 32, so a thread keeps its lane and the SELL slice addressing holds.
-template <int NCORR>
-__global__ void __launch_bounds__(TPB, 6)
-k_solve_fused(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, float4* xs_a, float4* xs_b,
-              const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
-              int iterations, double* __restrict__ rho_sum) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  const uint32_t stride = gridDim.x * TPB;
-  const uint32_t n_up = (n + 31u) & ~31u;                 // whole warps take part in the density reduction
-  for (int it = 0; it < iterations; it++) {
-    for (uint32_t t = blockIdx.x * TPB + threadIdx.x; t < n_up; t += stride) {
-      float rho = 0.f;
-      if (t < n) rho = lambda_particle<false>(P, t, i0 + t, xs_a, xs_b, nbr, slice_off, nbr_cnt, nullptr);
-      if (it == 0) block_sum_to_double(rho, rho_sum);
-    }
-    grid.sync();
-    for (uint32_t t = blockIdx.x * TPB + threadIdx.x; t < n; t += stride)
-      delta_particle<NCORR, false>(P, t, i0 + t, xs_b, xs_a, nbr, slice_off, nbr_cnt);
-    grid.sync();
-  }
+  delta_particle<NCORR, SPH>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt);
 }
 
 // ------------------------------------------------------------------------------------------------
 // G. finalize: velocity update (215-217), vorticity + XSPH + density (219-234, Jacobi, §7.3-3),
 //    confinement + commit (236-248)
 // ------------------------------------------------------------------------------------------------
+// Also writes the 32-byte record (x*, v) per particle that the vorticity/XSPH pass gathers with ONE 256-bit load
+// per pair (LDG.E.ENL2.256): a 32-byte gather costs 1.37x a 16-byte one, two 16-byte gathers from separate arrays
+// cost 2x (scripts/ubench/ffma2.cu, profiles/r01_ubench_ffma2_gather.txt).
 __global__ void __launch_bounds__(TPB)
 k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
-           const float4* __restrict__ pos, float4* __restrict__ vtmp) {
+           const float4* __restrict__ pos, float4* __restrict__ vtmp, float4* __restrict__ xv) {
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
   const float4 a = xs[i], b = pos[i];
-  vtmp[i] = make_float4(P.inv_dt * (a.x - b.x), P.inv_dt * (a.y - b.y), P.inv_dt * (a.z - b.z), 0.f);
+  const float4 v = make_float4(P.inv_dt * (a.x - b.x), P.inv_dt * (a.y - b.y), P.inv_dt * (a.z - b.z), 0.f);
+  vtmp[i] = v;
+  xv[2 * (size_t)i] = make_float4(a.x, a.y, a.z, 0.f);
+  xv[2 * (size_t)i + 1] = v;
+}
+
+// one 256-bit read-only gather of record j: (x*, v)
+__device__ __forceinline__ void ld_xv(const float4* __restrict__ xv, uint32_t j, float4& x, float4& v) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w), "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(xv + 2 * (size_t)j));
 }
 
 __global__ void __launch_bounds__(TPB)
 k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs,
-                 float4* __restrict__ xs_w, const float4* __restrict__ vtmp, float4* __restrict__ vel_out, float4* __restrict__ omega,
+                 float4* __restrict__ xs_w, const float4* __restrict__ vtmp, const float4* __restrict__ xv, float4* __restrict__ vel_out, float4* __restrict__ omega,
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
                  double* __restrict__ rho_sum) {
@@ -490,8 +504,8 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, 
     float w3s = 0.f, ox = 0.f, oy = 0.f, oz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
 #define BODY_V(J)                                                                     \
     {                                                                                 \
-      const float4 pj = __ldg(&xs[J]);                                                \
-      const float4 vj = __ldg(&vtmp[J]);                                              \
+      float4 pj, vj;                                                                  \
+      ld_xv(xv, J, pj, vj);                                                           \
       const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;               \
       const float ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;               \
       float r2, w3, g;                                                                \
@@ -766,10 +780,12 @@ void enqueue_predict_hash(Solver* h, int apply_forces) {
   cudaMemsetAsync(h->cell_of, 0xFF, sizeof(uint32_t) * h->n_in_cap(), h->stream);
   cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(h->sc->counters, 0, sizeof(h->sc->counters), h->stream);
-  LAUNCH(h, K_PREDICT, k_predict_hash, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur],
-         h->xs_tmp, h->cell_of, h->rank, h->cell_count, apply_forces,
-         h->slab && h->has_left ? h->mig_send[0] : (float4*)nullptr, h->slab && h->has_right ? h->mig_send[1] : (float4*)nullptr,
-         (uint32_t)h->halo_cap, h->sc);
+#define LAUNCH_PREDICT(KERN)                                                                                                      \
+  LAUNCH(h, K_PREDICT, KERN, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur], h->xs_tmp, h->cell_of, \
+         h->rank, h->cell_count, apply_forces, h->slab && h->has_left ? h->mig_send[0] : (float4*)nullptr,                            \
+         h->slab && h->has_right ? h->mig_send[1] : (float4*)nullptr, (uint32_t)h->halo_cap, h->sc)
+  if (h->dp.n_sph > 0) LAUNCH_PREDICT(k_predict_hash<true>); else LAUNCH_PREDICT(k_predict_hash<false>);
+#undef LAUNCH_PREDICT
 }
 
 // Phase 2: scan, scatter the n_in entries of the unsorted arrays that carry a valid cell, canonical
@@ -782,7 +798,9 @@ void enqueue_sort(Solver* h, size_t n_in) {
   LAUNCH(h, K_SCAN, k_scan_block_sums, 1, sb, h->block_sums);
   LAUNCH(h, K_SCAN, k_scan_apply, sb, ncell, h->cell_count, h->block_sums, h->cell_start);
   LAUNCH(h, K_SCATTER, k_scatter, blocks_for(n_in), (uint32_t)n_in, h->cell_of, h->rank, h->cell_start, h->orig[cur], h->perm, h->key);
-  LAUNCH(h, K_CELLSORT, k_cell_sort, blocks_for(ncell), ncell, h->cell_start, h->perm, h->key);
+  h->prof_begin(K_CELLSORT);
+  k_cell_sort<<<blocks_for(ncell, 128), 128, 0, h->stream>>>(ncell, h->cell_start, h->perm, h->key);
+  h->prof_end(K_CELLSORT); h->launches++;
   LAUNCH(h, K_REORDER, k_reorder, blocks_for(n_in), (uint32_t)n_in, h->cell_start + ncell, h->perm, h->key, h->pos[cur], h->vel[cur],
          h->xs_tmp, h->pos[nxt], h->vel[nxt], h->xs_a, h->orig[nxt]);
   h->cur = nxt;
@@ -791,7 +809,7 @@ void enqueue_sort(Solver* h, size_t n_in) {
 // Phase 3: frozen neighbour lists for the range [r_i0, r_i0 + r_cnt) of the n_sorted sorted particles.
 void enqueue_build(Solver* h, int include_self) {
   h->prof_begin(K_REORDER);
-  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega);
+  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega, h->xv);
   h->prof_end(K_REORDER); h->launches++;
   LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
          h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
@@ -825,18 +843,21 @@ void enqueue_delta(Solver* h, int part) {
   const int k = part_ranges(h, part, rng);
   for (int q = 0; q < k; q++) {
     const unsigned g = blocks_for(rng[q][1] - rng[q][0]);
-    if (h->dp.n_corr == 4) LAUNCH(h, K_DELTA, k_delta<4>, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
-    else LAUNCH(h, K_DELTA, k_delta<-1>, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt);
+#define LAUNCH_DELTA(KERN) LAUNCH(h, K_DELTA, KERN, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt)
+    const bool sph = h->dp.n_sph > 0;                  // box-only scenes run the instantiation without the sphere code
+    if (h->dp.n_corr == 4) { if (sph) LAUNCH_DELTA((k_delta<4, true>)); else LAUNCH_DELTA((k_delta<4, false>)); }
+    else { if (sph) LAUNCH_DELTA((k_delta<-1, true>)); else LAUNCH_DELTA((k_delta<-1, false>)); }
+#undef LAUNCH_DELTA
   }
 }
 void enqueue_velocity(Solver* h) {   // every sorted particle, ghosts included (their x and x* are bit-identical to the owner's)
-  LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp);
+  LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp, h->xv);
 }
 void enqueue_vorticity(Solver* h, int part) {
   uint32_t rng[2][2];
   const int k = part_ranges(h, part, rng);
   for (int q = 0; q < k; q++)
-    LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_tmp, h->vtmp,
+    LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_tmp, h->vtmp, h->xv,
            h->vel[h->cur], h->omega, h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
 }
 // velocity + XSPH + vorticity in the reference's sequential order, by fixed-point sweeps (single GPU)
@@ -863,41 +884,6 @@ void enqueue_vorticity_reference_order(Solver* h) {
 void enqueue_confine(Solver* h) {
   LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
          h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt);
-}
-
-// All iterations in one cooperative launch (single-GPU path; the slab path needs halo exchanges
-// between the passes).  Returns false when cooperative launch is unavailable or disabled
-// (the default; PBF_FUSED=1 enables it), in which case the caller issues the 2*I separate launches.
-bool enqueue_solve_fused(Solver* h) {
-  if (h->fused_state == 0) {
-    h->fused_state = -1;
-    const char* e = getenv("PBF_FUSED");
-    int coop = 0, sms = 0, nb4 = 0, nbg = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb4, k_solve_fused<4>, TPB, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbg, k_solve_fused<-1>, TPB, 0);
-    const int nb = h->dp.n_corr == 4 ? nb4 : nbg;
-    // Opt-in (PBF_FUSED=1).  Measured on B200 at 16M particles (profiles/r01_fused_vs_unfused.txt): the fused
-    // launch takes 102 ms against 63.8 ms for the 24 separate launches, because arrays produced and
-    // consumed inside one launch cannot be gathered through the read-only path (LDG.E.128.CONSTANT).
-    if (coop && nb > 0 && sms > 0 && e && atoi(e) == 1) { h->fused_state = 1; h->fused_grid = (unsigned)(nb * sms); }
-  }
-  if (h->fused_state != 1 || h->dp.iterations == 0) return false;
-  uint32_t i0 = h->r_i0, n = h->r_cnt;
-  int iters = h->dp.iterations;
-  double* rho_sum = &h->sc->rho_first;
-  void* args[] = {(void*)&h->dp, (void*)&i0, (void*)&n, (void*)&h->xs_a, (void*)&h->xs_b, (void*)&h->nbr, (void*)&h->slice_off,
-                  (void*)&h->nbr_cnt, (void*)&iters, (void*)&rho_sum};
-  const unsigned grid = std::min<unsigned>(h->fused_grid, std::max<unsigned>(1u, blocks_for(n)));
-  h->prof_begin(K_SOLVE_FUSED);
-  cudaError_t err = h->dp.n_corr == 4
-      ? cudaLaunchCooperativeKernel((void*)k_solve_fused<4>, dim3(grid), dim3(TPB), args, 0, h->stream)
-      : cudaLaunchCooperativeKernel((void*)k_solve_fused<-1>, dim3(grid), dim3(TPB), args, 0, h->stream);
-  h->prof_end(K_SOLVE_FUSED);
-  if (err != cudaSuccess) { cudaGetLastError(); h->fused_state = -1; return false; }   // fall back for good
-  h->launches++;
-  return true;
 }
 
 // single-GPU step: every particle is owned, n never changes, nothing needs a host round trip
@@ -932,8 +918,7 @@ void enqueue_step(Solver* h, bool readback) {
   enqueue_sort(h, n);
   enqueue_build(h, 0);
   if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
-  if (!enqueue_solve_fused(h))
-    for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
+  for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
   readback = readback && h->copy_stream && (h->rb_pos || h->rb_vel || h->rb_rho);
   if (readback) readback_piece(h, h->ev_rb[0], 0);          // positions are final once the iterations end
   enqueue_velocity(h);

@@ -10,7 +10,7 @@ ref = np.load(os.path.join(H.GOLDEN, "ref_jitter_two_blocks.npz"))
 g = api.Solver(api.default_params(rest_density=700.0))
 g.upload(ref["pos"], ref["vel"]); g.estimate_densities(); g.step(2)
 g.density_at(ref["pos"][:100]); g.step(1); g.neighbor_digest(); g.neighbors(); g.download()
-os.environ["PBF_FUSED"] = "1"
+os.environ["PBF_GRAPH"] = "0"
 g = api.Solver(api.default_params(rest_density=700.0)); g.upload(ref["pos"], ref["vel"]); g.step(2); g.download()
 s = slab.SlabSolver(api.default_params(rest_density=700.0), 0, 1)
 s.upload_local(ref["pos"], ref["vel"]); s.step(2); s.download_local(); s.neighbor_digest()

@@ -59,7 +59,7 @@ def test_library_is_cuda_and_loaded():
     assert s.launch_count() == 0
     pos, vel = lattice_block(4, 4, 4, origin=(-0.5, 0.2, -0.5))
     s.upload(pos, vel); s.step(1)
-    assert s.launch_count() >= 13    # sort (7) + sentinel + neighbours + solver (1 fused or 24) + 3 finalize
+    assert s.launch_count() >= 13    # sort (7) + sentinel + neighbours + solver (24) + 3 finalize
 
 
 @pytest.mark.parametrize("name", SHIPPED + JITTER)
