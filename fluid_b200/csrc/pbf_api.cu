@@ -49,6 +49,9 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.enable_vorticity = p.enable_vorticity; d.enable_xsph = p.enable_xsph;
   const float cell = d.h * (1.0f + 1.0f / 256.0f);
   d.inv_cell = 1.0f / cell;
+  d.zsub = 8;                                          // thin cells along z (measured: 1 / 4 / 8)
+  if (const char* e = getenv("PBF_ZSUB")) d.zsub = std::min(16, std::max(1, atoi(e)));
+  d.inv_cell_z = (float)d.zsub / cell;
   double ncell = 1;
   for (int a = 0; a < 3; a++) {
     if (!(p.box_max[a] > p.box_min[a])) { err = "empty box"; return PBF_ERR_INVALID; }
@@ -57,6 +60,7 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
     d.clo[a] = lo; d.chi[a] = hi;
     d.gmin[a] = d.bmin[a];
     d.gdim[a] = (int)std::floor((p.box_max[a] - p.box_min[a]) / (double)cell) + 1;
+    if (a == 2) d.gdim[a] *= d.zsub;
     ncell *= d.gdim[a];
   }
   d.yl = (float)p.y_light; d.zf = (float)p.z_front;

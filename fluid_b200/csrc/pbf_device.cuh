@@ -25,8 +25,12 @@ struct DevParams {
   float clo[3], chi[3];       // hard clamp bounds: bmin + eps_d, bmax - eps_d
   float yl, zf;               // virtual planes
   // uniform grid (cell edge slightly larger than h => 27-cell search is conservative)
+  // Along z (the fastest axis of the linear cell id) every cell is split into `zsub` thin cells of edge cell/zsub:
+  // the 27-cell neighbourhood is still 9 contiguous z-runs, but a run can be trimmed to the particle's reach at
+  // cell/zsub granularity instead of whole cells (35 % fewer candidates in the neighbour search at zsub = 8).
   float inv_cell; float gmin[3];
-  int   gdim[3];              // LOCAL cells per axis; linear id = (cx*gdim[1] + cy)*gdim[2] + cz  (z fastest)
+  float inv_cell_z; int zsub;
+  int   gdim[3];              // LOCAL cells per axis (z in thin cells); linear id = (cx*gdim[1] + cy)*gdim[2] + cz  (z fastest)
   // slab decomposition along x: the grid is global (same gmin / inv_cell on every rank, so a
   // position maps to the same cell everywhere); this rank stores columns cx_offset .. cx_offset+gdim[0]-1
   // and owns the global columns [gx_lo, gx_hi).  Single GPU: cx_offset 0, owns everything.
@@ -171,11 +175,12 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
 
 // Cell coordinates of a position (clamped into the grid).  Conservative for the 27-cell search
 // because the cell edge is h*(1+2^-8) and fp32 rounding of (x-gmin)*inv_cell is << 2^-9 cells
-// for the domains we support (<= 2^12 cells per axis).
+// for the domains we support (<= 2^12 cells per axis).  z is in thin cells (see DevParams::zsub); the search
+// derives its z-range from the particle's z, not from +-1 cell.
 __device__ __forceinline__ int3 cell_coords_global(const DevParams& P, float x, float y, float z) {
   int cx = (int)floorf((x - P.gmin[0]) * P.inv_cell);
   int cy = (int)floorf((y - P.gmin[1]) * P.inv_cell);
-  int cz = (int)floorf((z - P.gmin[2]) * P.inv_cell);
+  int cz = (int)floorf((z - P.gmin[2]) * P.inv_cell_z);
   cx = min(max(cx, 0), P.gdim_x_global - 1);
   cy = min(max(cy, 0), P.gdim[1] - 1);
   cz = min(max(cz, 0), P.gdim[2] - 1);

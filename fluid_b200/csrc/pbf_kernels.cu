@@ -149,10 +149,35 @@ k_scatter(uint32_t n, const uint32_t* __restrict__ cell_of, const uint32_t* __re
 // by their original id makes the whole layout (and therefore every floating-point sum downstream)
 // a pure function of the particle state: runs are bit-reproducible, and a slab decomposition sees
 // the same order as one GPU does.
-// One thread per cell.  Up to 32 particles (a lattice at spacing h/3 has 27 per cell): the (id, slot) pairs are
-// loaded into registers as 64-bit words and sorted by a fully unrolled 32-input bitonic network (240 compare-
-// exchanges, compile-time indices, no memory traffic); unused inputs hold +inf.  Fuller cells fall back to an
-// insertion sort in global memory.
+// One thread per (thin) cell.  The cell's (id, slot) pairs are loaded into registers as 64-bit words and sorted by a
+// fully unrolled N-input bitonic network (compile-time indices, no memory traffic), N = 8 / 16 / 32 by occupancy
+// (thin cells of a lattice at spacing h/3 hold 3-4 particles); unused inputs hold +inf.  Fuller cells fall back to
+// an insertion sort in global memory.
+template <int N>
+__device__ __forceinline__ void cell_sort_network(uint32_t s, uint32_t cnt, uint32_t* __restrict__ perm, uint32_t* __restrict__ key) {
+  unsigned long long v[N];
+#pragma unroll
+  for (int k = 0; k < N; k++)
+    v[k] = (uint32_t)k < cnt ? ((unsigned long long)key[s + k] << 32) | perm[s + k] : ~0ull;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const unsigned long long a = v[i], b = v[l];
+          const bool sw = (a > b) == up;
+          v[i] = sw ? b : a; v[l] = sw ? a : b;
+        }
+      }
+#pragma unroll
+  for (int k = 0; k < N; k++)
+    if ((uint32_t)k < cnt) { key[s + k] = (uint32_t)(v[k] >> 32); perm[s + k] = (uint32_t)v[k]; }
+}
+
 __global__ void __launch_bounds__(128)
 k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ perm,
             uint32_t* __restrict__ key) {
@@ -161,30 +186,9 @@ k_cell_sort(uint32_t ncell, const uint32_t* __restrict__ cell_start, uint32_t* _
   const uint32_t s = cell_start[c], e = cell_start[c + 1];
   const uint32_t cnt = e - s;
   if (cnt <= 1u) return;
-  if (cnt <= 32u) {
-    unsigned long long v[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++)
-      v[k] = (uint32_t)k < cnt ? ((unsigned long long)key[s + k] << 32) | perm[s + k] : ~0ull;
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1)
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const int l = i ^ j;
-          if (l > i) {
-            const bool up = (i & k) == 0;
-            const unsigned long long a = v[i], b = v[l];
-            const bool sw = (a > b) == up;
-            v[i] = sw ? b : a; v[l] = sw ? a : b;
-          }
-        }
-#pragma unroll
-    for (int k = 0; k < 32; k++)
-      if ((uint32_t)k < cnt) { key[s + k] = (uint32_t)(v[k] >> 32); perm[s + k] = (uint32_t)v[k]; }
-    return;
-  }
+  if (cnt <= 8u) { cell_sort_network<8>(s, cnt, perm, key); return; }
+  if (cnt <= 16u) { cell_sort_network<16>(s, cnt, perm, key); return; }
+  if (cnt <= 32u) { cell_sort_network<32>(s, cnt, perm, key); return; }
   for (uint32_t a = s + 1; a < e; a++) {
     const uint32_t k = key[a], p = perm[a];
     uint32_t b = a;
@@ -242,7 +246,7 @@ __device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, 
 
 // Candidate range [b, e) of z-run k (k = 3*(dx+1) + (dy+1)) for a particle at pi in cell c, with
 // conservative culling: the run is dropped when the (dx,dy) cell column is farther than h in the
-// xy-plane, and its z-extent is trimmed to the cells that can still reach the particle.  `slack`
+// xy-plane, and its z-extent is trimmed to the thin cells that can still reach the particle.  `slack`
 // covers the fp32 rounding of the cell assignment (a particle may sit a few ulp outside the
 // nominal bounds of its cell), so no true neighbour is ever culled; the exact predicate decides.
 __device__ __forceinline__ void nb_run_range(const DevParams& P, const uint32_t* __restrict__ cell_start, float3 pi, int3 c, int k,
@@ -259,10 +263,11 @@ __device__ __forceinline__ void nb_run_range(const DevParams& P, const uint32_t*
   dx = fmaxf(dx - slack, 0.f); dy = fmaxf(dy - slack, 0.f);
   const float rz2 = P.h2 - (dx * dx + dy * dy);
   if (rz2 < 0.f) return;
-  const float z_lo = P.gmin[2] + (float)c.z * cell;
-  const float dzl = fmaxf(pi.z - z_lo - slack, 0.f), dzh = fmaxf((z_lo + cell) - pi.z - slack, 0.f);
-  const int zlo = (c.z > 0 && dzl * dzl <= rz2) ? c.z - 1 : c.z;
-  const int zhi = (c.z < P.gdim[2] - 1 && dzh * dzh <= rz2) ? c.z + 1 : c.z;
+  // z-extent of the particle's reach inside this column, in thin cells (monotonic in z, so every candidate with
+  // |z_j - z_i| <= rz lies in [zlo, zhi]; the slack covers the roundings of rz and of the cell index)
+  const float rz = sqrtf(rz2) + slack;
+  const int zlo = max((int)floorf((pi.z - rz - P.gmin[2]) * P.inv_cell_z), 0);
+  const int zhi = min((int)floorf((pi.z + rz - P.gmin[2]) * P.inv_cell_z), P.gdim[2] - 1);
   const uint32_t base = (uint32_t)((cx * P.gdim[1] + cy) * P.gdim[2]);
   b = cell_start[base + zlo];
   e = cell_start[base + zhi + 1];
@@ -661,7 +666,9 @@ k_density_at(const __grid_constant__ DevParams P, uint32_t m, const float4* __re
   if (t >= m) return;
   const float4 pi = q[t];
   const int3 c = cell_coords(P, pi.x, pi.y, pi.z);
-  const int zlo = max(c.z - 1, 0), zhi = min(c.z + 1, P.gdim[2] - 1);
+  const float reach = P.h * (1.f + 1e-3f) + 1e-6f * fabsf(pi.z);
+  const int zlo = max((int)floorf((pi.z - reach - P.gmin[2]) * P.inv_cell_z), 0);
+  const int zhi = min((int)floorf((pi.z + reach - P.gmin[2]) * P.inv_cell_z), P.gdim[2] - 1);
   float w3s = 0.f;
 #pragma unroll 1
   for (int k = 0; k < 9; k++) {

@@ -79,7 +79,8 @@ def test_grid_dims_and_columns_on_host():
     dims = (C.c_int * 3)()
     assert lib.pbf_grid_dims(C.byref(p), C.byref(dims)) == 0
     cell = np.float32(0.3) * (np.float32(1) + np.float32(1 / 256))
-    assert list(dims) == [int(np.floor(120.0 / float(cell))) + 1, int(np.floor(30.0 / float(cell))) + 1, int(np.floor(20.1 / float(cell))) + 1]
+    zsub = int(os.environ.get("PBF_ZSUB", "8"))     # thin cells along z (DevParams::zsub)
+    assert list(dims) == [int(np.floor(120.0 / float(cell))) + 1, int(np.floor(30.0 / float(cell))) + 1, (int(np.floor(20.1 / float(cell))) + 1) * zsub]
     x = np.array([[0.0, 1, 1], [0.30, 1, 1], [0.302, 1, 1], [119.99, 1, 1], [500.0, 1, 1]])
     col = np.empty(5, dtype=np.int32)
     assert lib.pbf_cell_columns(C.byref(p), 5, x.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p)) == 0

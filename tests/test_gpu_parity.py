@@ -201,19 +201,29 @@ def test_deterministic():
 
 def test_rollout_drift_vs_fp64_oracle():
     """Free-running rollouts: per-particle comparison is meaningless after a few steps (chaos,
-    SURVEY.md §7.3-5); aggregates must stay close.  Gates calibrated with the two CPU oracles
-    against each other on this 2106-particle sloshing scene (fp32 vs fp64, same algorithm):
-    kinetic energy agrees to 1 % at step 25 but only to 30-70 % at steps 50-100 (a few fast
-    particles dominate), mean density to 0.15 %, centre of mass to 0.006 / 0.027 (steps 25 / 100).
-    So KE is gated at step 25 and only density / centre of mass / sanity at step 100."""
+    SURVEY.md §7.3-5); aggregates must stay close.  Gates calibrated on this 2106-particle sloshing scene:
+    around step 25 the kinetic energy falls by ~9 % per step (2093 -> 830 over steps 20-30), the two CPU oracles
+    (fp32 vs fp64, same summation order) are up to 11 % apart in that window, and GPU runs that differ ONLY in
+    the in-cell particle order (PBF_ZSUB = 1 / 2 / 8, i.e. in fp32 summation order) give 1311 / 1195 / 1129 at
+    step 25 against 1379 (fp64 oracle) - scripts/evolved_check.py.  So KE is gated at 30 % there, mean density to
+    1 % (oracles: 0.15 %), centre of mass to 0.01 / 0.03 of the box diagonal (oracles: 0.006 / 0.027 at steps
+    25 / 100); at steps 50-100 KE is only sanity-checked (a few fast particles dominate).
+    What IS exact along the rollout: the neighbour sets of the evolved, disordered states (teacher-forced
+    against the fp32 oracle every 5 steps)."""
     pos, vel, rho0, _ = _scene("two_blocks")
     diag = np.linalg.norm([2.0, 1.49, 2.0])
     g = _gpu(rho0); g.upload(pos, vel)
     o = _oracle(rho0, 64); o.upload(pos, vel)
-    g.step(25); o.step(25)
+    for _ in range(5):
+        g.step(5)
+        P, V, _r = g.download()
+        g0 = _gpu(rho0, iterations=0); g0.upload(P, V); g0.step(1)
+        o0 = _oracle(rho0, 32, iterations=0); o0.upload(P, V); o0.step(1)
+        assert np.array_equal(g0.neighbor_digest()[0], o0.digest()[0]), "neighbour sets of an evolved state differ from the fp32 oracle"
+    o.step(25)
     Pg, Vg, Rg = g.download(); Po, Vo, Ro = o.download()
     keg, keo = 0.5 * (Vg ** 2).sum(), 0.5 * (Vo ** 2).sum()
-    assert abs(keg - keo) <= 0.05 * keo, (keg, keo)
+    assert abs(keg - keo) <= 0.30 * keo, (keg, keo)
     assert abs(Rg.mean() - Ro.mean()) / rho0 <= 0.01
     assert np.linalg.norm(Pg.mean(axis=0) - Po.mean(axis=0)) <= 0.01 * diag
     g.step(75); o.step(75)
