@@ -362,14 +362,22 @@ __global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, floa
 // Visit the frozen neighbours of the calling thread's particle: body(p_j float4, extra...) is
 // applied to 4 gathered neighbours per coalesced uint4 index load, with the next index row
 // prefetched while the current one is processed.
+// The list rows are read exactly once per pass: they bypass L1 allocation (LDG.E.NA) so that they do not evict the
+// neighbour positions, which ARE reused (measured: -2.5 % per step; an L2 evict-first policy on the same loads or
+// evict-last on the gathers did not help, profiles/r01_cache_policy_ab.txt).
+__device__ __forceinline__ uint4 ld_list_row(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 #define PBF_FOR_NEIGHBORS(t, BODY)                                                                   \
   {                                                                                                  \
     const uint4* lst_ = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[(t) >> 5] * 32u + (threadIdx.x & 31); \
     const uint32_t rows_ = (nbr_cnt[t] + 3u) >> 2;                                                   \
-    uint4 nx_ = rows_ ? __ldg(lst_) : make_uint4(0, 0, 0, 0);                                        \
+    uint4 nx_ = rows_ ? ld_list_row(lst_) : make_uint4(0, 0, 0, 0);                                  \
     for (uint32_t r_ = 0; r_ < rows_; r_++) {                                                        \
       const uint4 jj_ = nx_;                                                                         \
-      if (r_ + 1 < rows_) nx_ = __ldg(lst_ + (size_t)(r_ + 1) * 32u);                                \
+      if (r_ + 1 < rows_) nx_ = ld_list_row(lst_ + (size_t)(r_ + 1) * 32u);                          \
       BODY(jj_.x) BODY(jj_.y) BODY(jj_.z) BODY(jj_.w)                                                \
     }                                                                                                \
   }
@@ -548,7 +556,7 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
     float ex = 0.f, ey = 0.f, ez = 0.f;
 #define BODY_C(J)                                                          \
     {                                                                      \
-      const float4 pj = __ldg(&xs[J]);                                     \
+      const float4 pj = __ldg(&xs[J]);                                 \
       const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;    \
       float r2, w3, g;                                                     \
       pair_terms(P, dx, dy, dz, r2, w3, g);                                \
