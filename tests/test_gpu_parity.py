@@ -441,6 +441,26 @@ def test_obstacle_spheres_keep_particles_out_and_api_errors():
         g.set_obstacle_spheres([[0.0, 0.3, 0.0, -0.1]])
 
 
+def test_thin_cell_count_changes_order_not_sets(monkeypatch):
+    """The cell grid is split into PBF_ZSUB thin cells along z (search culling + in-cell order).  Any value must give
+    the same neighbour SETS and predicted positions (exact) and the same step up to fp32 summation order."""
+    out = {}
+    for name in ("corner", "sphere_hit"):
+        ref = np.load(os.path.join(GOLDEN, f"ref_{name}.npz" if name.startswith("sphere") else f"ref_jitter_{name}.npz"))
+        pos, vel, rho0 = ref["state_1"][:, 0:3], ref["state_1"][:, 3:6], float(ref["rho0"])
+        for z in ("1", "3", "8", "16"):
+            monkeypatch.setenv("PBF_ZSUB", z)
+            g = _gpu(rho0); g.capture(True)
+            if "spheres" in ref.files:
+                g.set_obstacle_spheres(ref["spheres"])
+            g.upload(pos, vel); g.step(1)
+            out[z] = (g.array(ARRAY_XPRED), g.neighbor_digest(), g.download())
+        for z in ("1", "3", "16"):
+            assert np.array_equal(out[z][0], out["8"][0]), (name, z)
+            assert np.array_equal(out[z][1][0], out["8"][1][0]) and np.array_equal(out[z][1][1], out["8"][1][1]), (name, z)
+            _gate_whole_step(f"{name}/zsub{z} vs zsub8", out[z][2][0], out[z][2][2], out["8"][2][0], out["8"][2][2], rho0)
+
+
 def test_graph_replay_equals_plain_launches(monkeypatch):
     """Launch-bound scenes replay the step as a CUDA graph (one per buffer parity, PBF_GRAPH): the state after
     7 steps, a re-upload and 3 more steps is bit-identical to plain launches, and launch_count() still counts
