@@ -66,7 +66,7 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.yl = (float)p.y_light; d.zf = (float)p.z_front;
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
-  d.n_sph = 0;
+  d.n_sph = 0; d.n_sm = 148;
   for (int k = 0; k < PBF_MAX_SPHERES; k++) { d.sph[k] = make_float4(0.f, 0.f, 0.f, 0.f); d.sph_r2[k] = 0.f; }
   return PBF_OK;
 }
@@ -223,6 +223,7 @@ int pbf_create(const PbfParams* params, int device_id, pbf_handle** out) {
   int rc = fill_dev_params(*params, h->dp, err);
   if (rc != PBF_OK) { fprintf(stderr, "pbf_create: %s\n", err.c_str()); delete h; return rc; }
   h->ncell = (uint32_t)((size_t)h->dp.gdim[0] * h->dp.gdim[1] * h->dp.gdim[2]);
+  { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id) == cudaSuccess && sms > 0) h->dp.n_sm = sms; }
   auto bail = [&](cudaError_t e) { fprintf(stderr, "pbf_create: %s\n", cudaGetErrorString(e)); delete h; return PBF_ERR_CUDA; };
   cudaError_t e;
   if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e);

@@ -36,6 +36,7 @@ struct DevParams {
   // and owns the global columns [gx_lo, gx_hi).  Single GPU: cx_offset 0, owns everything.
   int   gdim_x_global, cx_offset, gx_lo, gx_hi, hop_left, hop_right;
   // obstacle spheres (pbf_set_obstacle_spheres): centre xyz, radius in .w; r^2 = r*r rounded once
+  int   n_sm;                 // SMs of the device (tile order of the gather kernels)
   int   n_sph;
   float4 sph[8];
   float sph_r2[8];

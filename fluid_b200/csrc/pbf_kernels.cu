@@ -423,12 +423,24 @@ __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t,
   return rho;
 }
 
-__global__ void __launch_bounds__(TPB)
+// Tile order of the gather kernels.  Blocks are handed to the SMs round-robin, so with the identity mapping SM s
+// holds tiles s, s + n_sm, s + 2 n_sm, ... of the active window.  Inside every group of n_sm * 6 blocks (6 = resident
+// CTAs per SM) the tile index is transposed, so that the CTAs resident on one SM work on ADJACENT tiles and share
+// their neighbourhood lines in L1: lambda 2.56 -> 2.42 ms (the other gather kernels are unchanged; any group
+// width 2..48 gives the same gain, profiles/r01_cache_policy_ab.txt).  Particles are independent within a pass,
+// so the order has no effect on the results.
+__device__ __forceinline__ uint32_t tile_of_block(const DevParams& P) {
+  const uint32_t C = 6u, G = (uint32_t)P.n_sm * C, b = blockIdx.x, g = b / G, r = b % G;
+  if ((g + 1u) * G > gridDim.x) return b;                 // tail group stays as is
+  return g * G + (r % (uint32_t)P.n_sm) * C + (r / (uint32_t)P.n_sm);
+}
+
+__global__ void __launch_bounds__(TPB)      // 40 registers, 6 CTAs per SM; forcing 32 registers / 8 CTAs measured no faster
 k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multiple of 32 */, uint32_t n /* end of the t range */,
          const float4* __restrict__ xs_in,
          float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
          const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
-  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   float rho = 0.f;
   if (t < n) rho = lambda_particle(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out);
   if (rho_sum) block_sum_to_double(rho, rho_sum);
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(TPB)
 k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
         const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   if (t >= n) return;
   delta_particle<NCORR, SPH>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt);
 }
@@ -508,7 +520,7 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, 
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
                  double* __restrict__ rho_sum) {
-  const uint32_t t = t0 + blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   float rho = 0.f;
   if (t < n) {
@@ -548,7 +560,7 @@ k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, c
                  const float4* __restrict__ omega, float4* __restrict__ vel, float4* __restrict__ pos,
                  const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
                  const uint32_t* __restrict__ nbr_cnt) {
-  const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t t = tile_of_block(P) * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   if (t >= n) return;
   const float4 pi = xs[i];
