@@ -64,6 +64,12 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
     ncell *= d.gdim[a];
   }
   d.yl = (float)p.y_light; d.zf = (float)p.z_front;
+  for (int a = 0; a < 3; a++) {   // collide fast path: inside these bounds (both ends of a move) nothing can be hit
+    const float margin = 1e-4f * (1.0f + std::max(std::fabs(d.bmin[a]), std::fabs(d.bmax[a])));
+    d.slo[a] = d.bmin[a] + margin; d.shi[a] = d.bmax[a] - margin;
+  }
+  d.shi[1] = std::min(d.shi[1], d.yl - 1e-4f * (1.0f + std::fabs(d.yl)));
+  d.shi[2] = std::min(d.shi[2], d.zf - 1e-4f * (1.0f + std::fabs(d.zf)));
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
   d.n_sph = 0; d.n_sm = 148;
