@@ -217,15 +217,14 @@ k_reorder(uint32_t n_upper, const uint32_t* __restrict__ n_sorted_ptr, const uin
 // indices) per lane, so entry s of lane l lives at nbr[(slice_off + s/4)*128 + 4*l + s%4] and
 // every later pass reads its indices as fully coalesced 16-byte loads.  Lists are padded to a
 // multiple of 4 with the sentinel index n (a particle parked far outside the domain, so it adds
-// exactly 0 to every sum).  Two passes over the 9 z-runs of candidates (count, then fill) — no
-// truncation, ever.
+// exactly 0 to every sum).  No truncation, ever: overflow of the row pool is an error.
 // ------------------------------------------------------------------------------------------------
 // Single pass over the candidates: the predicate results are kept as bitmasks (one word per 32
 // candidates of a z-run, parked in thread-local memory: one store per 32 candidates), the counts
 // come from popc, rows are allocated with one atomic per slice, and the fill phase just walks
 // the set bits.  Candidates are evaluated in unconditional groups of 8 (reads past the end of a
 // run are in-bounds of the padded arrays and masked off), so the inner loop has no bounds checks.
-static constexpr int NB_TOTW = 48;      // cached mask words per particle (a lattice at spacing h/3 needs 27);
+static constexpr int NB_TOTW = 48;      // cached mask words per particle (a lattice at spacing h/3 needs about 20 with thin z-cells);
                                         // crowded neighbourhoods recompute the words beyond that in the fill phase
 
 __device__ __forceinline__ uint32_t nb_eval_word(const float4* __restrict__ xs, float3 pi, float h2, uint32_t wb, uint32_t lim) {
