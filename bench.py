@@ -305,7 +305,7 @@ def main():
         else:
             capn = int(solver.particle_cap)
             P = np.empty((capn, 3)); V = np.empty((capn, 3)); R = np.empty(capn); I = np.empty(capn, dtype=np.uint32)
-            solver.pin(P, V, R)
+            solver.pin(P, V, R, I)
             nl = solver.download_local_into(P, V, R, I)
             barrier(); t0 = time.perf_counter()
             for _ in range(k2):
