@@ -62,6 +62,7 @@ def load_library():
         "pbf_host_unregister": (i32, [vp, vp]),
         "pbf_set_readback": (i32, [vp, vp, vp, vp]),
         "pbf_set_obstacle_spheres": (i32, [vp, sz, vp]),
+        "pbf_set_obstacle_triangles": (i32, [vp, sz, vp]),
         "pbf_step": (i32, [vp, i32]),
         "pbf_sync": (i32, [vp]),
         "pbf_estimate_densities": (i32, [vp]),
@@ -151,6 +152,11 @@ class Solver:
         """Obstacle spheres of the collision scene, rows (cx, cy, cz, r); an empty list removes them."""
         sp = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
         self._ck(self.lib.pbf_set_obstacle_spheres(self.h, sp.shape[0], _ptr(sp)))
+
+    def set_obstacle_triangles(self, tris):
+        """Obstacle triangles, rows of 18 (p1, p2, p3, n1, n2, n3); an empty list removes them."""
+        t = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
+        self._ck(self.lib.pbf_set_obstacle_triangles(self.h, t.shape[0], _ptr(t)))
 
     def upload_device(self, n, d_pos_ptr, d_vel_ptr):
         self.n = n

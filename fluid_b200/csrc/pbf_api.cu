@@ -72,7 +72,8 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.shi[2] = std::min(d.shi[2], d.zf - 1e-4f * (1.0f + std::fabs(d.zf)));
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
-  d.n_sph = 0; d.n_sm = 148;
+  d.n_sph = 0; d.n_sm = 148; d.n_tri = 0; d.tri = nullptr;
+  for (int a = 0; a < 3; a++) { d.tlo[a] = 0.f; d.thi[a] = 0.f; }
   for (int k = 0; k < PBF_MAX_SPHERES; k++) { d.sph[k] = make_float4(0.f, 0.f, 0.f, 0.f); d.sph_r2[k] = 0.f; }
   return PBF_OK;
 }
@@ -259,6 +260,7 @@ void pbf_destroy(pbf_handle* h) {
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   delete static_cast<HandleExtra*>(h->host_extra);
+  cudaFree(h->tri_dev);
   delete h;
 }
 
@@ -420,6 +422,49 @@ int pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* s) {
     h->dp.sph[k] = make_float4((float)s[4 * k], (float)s[4 * k + 1], (float)s[4 * k + 2], r);
     h->dp.sph_r2[k] = r2;
   }
+  return PBF_OK;
+}
+
+// Obstacle triangles (small meshes; every particle whose move touches the mesh's bounding box tests all of them).
+// Edges, orientation and |e1 x e2| are precomputed in fp32 with the same single roundings as Oracle<float>::set_triangles.
+int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
+  if (!h || (count && !q)) return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_triangles: null argument");
+  if (count > PBF_MAX_TRIANGLES) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_triangles: more than PBF_MAX_TRIANGLES triangles");
+  for (size_t k = 0; k < 18 * count; k++) if (!std::isfinite(q[k])) return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_triangles: non-finite value");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));            // kernels in flight still read the old list
+  h->graph_invalidate();
+  if (h->tri_dev) { cudaFree(h->tri_dev); h->tri_dev = nullptr; }
+  h->dp.n_tri = 0; h->dp.tri = nullptr;
+  if (count == 0) return PBF_OK;
+  std::vector<float> t(20 * count);
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  for (size_t k = 0; k < count; k++) {
+    volatile float v[18];
+    for (int a = 0; a < 18; a++) v[a] = (float)q[18 * k + a];
+    volatile float e1[3], e2[3], ng[3];
+    for (int a = 0; a < 3; a++) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
+    { volatile float m1 = e1[1] * e2[2], m2 = e1[2] * e2[1]; ng[0] = m1 - m2; }
+    { volatile float m1 = e1[2] * e2[0], m2 = e1[0] * e2[2]; ng[1] = m1 - m2; }
+    { volatile float m1 = e1[0] * e2[1], m2 = e1[1] * e2[0]; ng[2] = m1 - m2; }
+    volatile float ns[3];
+    for (int a = 0; a < 3; a++) { volatile float s1 = v[9 + a] + v[12 + a]; ns[a] = s1 + v[15 + a]; }
+    volatile float d0 = ng[0] * ns[0], d1 = ng[1] * ns[1], d2 = ng[2] * ns[2];
+    volatile float dsum = d0 + d1; dsum = dsum + d2;
+    volatile float q0 = ng[0] * ng[0], q1 = ng[1] * ng[1], q2 = ng[2] * ng[2];
+    volatile float qs = q0 + q1; qs = qs + q2;
+    float* o = &t[20 * k];
+    for (int a = 0; a < 3; a++) { o[a] = v[a]; o[3 + a] = e1[a]; o[6 + a] = e2[a]; }
+    for (int a = 0; a < 9; a++) o[9 + a] = v[9 + a];
+    o[18] = dsum < 0.f ? -1.f : 1.f;                    // orientation of e1 x e2 against the vertex normals
+    o[19] = std::sqrt((float)qs);                       // |e1 x e2|
+    for (int p3 = 0; p3 < 3; p3++) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], (float)v[3 * p3 + a]); hi[a] = std::max(hi[a], (float)v[3 * p3 + a]); }
+  }
+  CK(h, cudaMalloc((void**)&h->tri_dev, t.size() * sizeof(float)));
+  CK(h, cudaMemcpy(h->tri_dev, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float margin = 1e-2f * h->dp.h;               // >> the contact tolerance (1e-4 h) and the inflated edges
+  for (int a = 0; a < 3; a++) { h->dp.tlo[a] = lo[a] - margin - 1e-5f * std::fabs(lo[a]); h->dp.thi[a] = hi[a] + margin + 1e-5f * std::fabs(hi[a]); }
+  h->dp.tri = h->tri_dev; h->dp.n_tri = (int)count;
   return PBF_OK;
 }
 

@@ -38,6 +38,11 @@ struct DevParams {
   int   gdim_x_global, cx_offset, gx_lo, gx_hi, hop_left, hop_right;
   // obstacle spheres (pbf_set_obstacle_spheres): centre xyz, radius in .w; r^2 = r*r rounded once
   int   n_sm;                 // SMs of the device (tile order of the gather kernels)
+  // obstacle triangles (pbf_set_obstacle_triangles): 5 float4 each = p1, e1 = p2-p1, e2 = p3-p1, n1, n2, n3, sg, ngl
+  // (sg = +-1 orientation of e1 x e2 against the vertex normals, ngl = |e1 x e2|); tlo / thi = bounding box + margin
+  const float4* tri;
+  int   n_tri;
+  float tlo[3], thi[3];
   int   n_sph;
   float4 sph[8];
   float sph_r2[8];
@@ -114,12 +119,51 @@ __device__ __forceinline__ bool ex_sphere_hit(const DevParams& P, float3 o, floa
   return hit;
 }
 
+// One-sided obstacle triangles (Moller-Trumbore as marching_triangle.cpp:21-73): mirrors
+// Oracle<float>::mesh_hit_onesided operation for operation.  `slid` = the triangle being slid on (re-tested, but it
+// blocks only a direction that dips below its plane by more than TAN: the slide direction comes from the
+// interpolated vertex normals and may point into the surface).
+__device__ __forceinline__ float3 ex_cross(float3 u, float3 v) {
+  return make_float3(__fsub_rn(__fmul_rn(u.y, v.z), __fmul_rn(u.z, v.y)), __fsub_rn(__fmul_rn(u.z, v.x), __fmul_rn(u.x, v.z)),
+                     __fsub_rn(__fmul_rn(u.x, v.y), __fmul_rn(u.y, v.x)));
+}
+__device__ __forceinline__ bool ex_mesh_hit(const DevParams& P, float3 o, float3 d, float& max_t, int& which, float3& nrm, int slid) {
+  // bounding-box reject: a hit point (or a contact within TOL_T) lies inside the mesh's box, which the segment must touch
+  const float3 q = make_float3(o.x + max_t * d.x, o.y + max_t * d.y, o.z + max_t * d.z);
+  if (fmaxf(o.x, q.x) < P.tlo[0] || fminf(o.x, q.x) > P.thi[0] || fmaxf(o.y, q.y) < P.tlo[1] || fminf(o.y, q.y) > P.thi[1] ||
+      fmaxf(o.z, q.z) < P.tlo[2] || fminf(o.z, q.z) > P.thi[2]) return false;
+  const float BT = 1e-6f, ONE_BT = __fadd_rn(1.f, 1e-6f), TOL_T = __fmul_rn(1e-4f, P.h), TAN = 1e-5f;
+  bool hit = false;
+  for (int k = 0; k < P.n_tri; k++) {
+    const float4* T = P.tri + 5 * k;
+    const float4 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2);
+    const float3 p1 = make_float3(a0.x, a0.y, a0.z), e1 = make_float3(a0.w, a1.x, a1.y), e2 = make_float3(a1.z, a1.w, a2.x);
+    const float3 s = make_float3(__fsub_rn(o.x, p1.x), __fsub_rn(o.y, p1.y), __fsub_rn(o.z, p1.z));
+    const float3 s1 = ex_cross(d, e2), s2 = ex_cross(s, e1);
+    const float dd = ex_dot(s1, e1);
+    const float4 a3 = __ldg(T + 3), a4 = __ldg(T + 4);
+    const float sg = a4.z, ngl = a4.w;
+    if (!(__fmul_rn(sg, dd) > (k == slid ? __fmul_rn(TAN, ngl) : 0.f))) continue;
+    float t = __fdiv_rn(ex_dot(s2, e2), dd);
+    if (t < 0.f) { if (t >= -TOL_T) t = 0.f; else continue; }
+    if (t > max_t) continue;
+    const float u = __fdiv_rn(ex_dot(s1, s), dd), v = __fdiv_rn(ex_dot(s2, d), dd), w = __fsub_rn(__fsub_rn(1.f, u), v);
+    if ((u < -BT) || (u > ONE_BT) || (v < -BT) || (v > ONE_BT) || (w < -BT) || (w > ONE_BT)) continue;
+    const float3 n1 = make_float3(a2.y, a2.z, a2.w), n2 = make_float3(a3.x, a3.y, a3.z), n3 = make_float3(a3.w, a4.x, a4.y);
+    max_t = t; which = k; hit = true;
+    nrm = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(w, n1.x), __fmul_rn(u, n2.x)), __fmul_rn(v, n3.x)),
+                      __fadd_rn(__fadd_rn(__fmul_rn(w, n1.y), __fmul_rn(u, n2.y)), __fmul_rn(v, n3.y)),
+                      __fadd_rn(__fadd_rn(__fmul_rn(w, n1.z), __fmul_rn(u, n2.z)), __fmul_rn(v, n3.z)));
+  }
+  return hit;
+}
+
 // Swept move of p by delta against the box: clamp() (respond=false, particles.cpp:51-84) and
 // clamp_response() (respond=true: slide once along the wall, particles.cpp:87-132), with the
 // fp32 contact rules of SURVEY.md §7.3-4 (one-sided planes, exact axis normals, sticky virtual
 // planes).  Mirrors Oracle<float>::collide(COLLIDE_ANALYTIC_BOX) operation for operation.
-// SPH: obstacle spheres compiled in (the kernels are instantiated both ways and the box-only build is launched when
-// the scene has no spheres, so box-only scenes pay nothing for them).
+// SPH: obstacles (spheres, triangles) compiled in (the kernels are instantiated both ways and the box-only build is
+// launched when the scene has none, so box-only scenes pay nothing for them).
 template <bool SPH>
 __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float3 delta, bool respond) {
   if (!SPH) {
@@ -140,10 +184,11 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
     bool virt = false;
     if (d.z > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.zf, p.z), d.z); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
     if (d.y > 0.f) { float pt = __fdiv_rn(__fsub_rn(P.yl, p.y), d.y); if (pt >= 0.f && pt < l) { l = pt; virt = true; } }
-    float max_t = l; int axis = -1, side = 0, sph = -1;
+    float max_t = l; int axis = -1, side = 0, sph = -1, tri = -1;
     float3 sn = make_float3(0.f, 0.f, 0.f);
     bool hit = ex_box_hit(P, p, d, max_t, axis, side, -1, 0);
-    if (SPH && ex_sphere_hit(P, p, d, max_t, sph, sn, -1)) hit = true;           // nearest of walls and spheres
+    if (SPH && ex_sphere_hit(P, p, d, max_t, sph, sn, -1)) hit = true;           // nearest of walls, spheres and triangles
+    if (SPH && P.n_tri > 0 && ex_mesh_hit(P, p, d, max_t, tri, sn, -1)) { hit = true; sph = -1; }
     if (hit || virt) {
       const float s = __fsub_rn(max_t, P.eps_d);
       p.x = __fadd_rn(p.x, __fmul_rn(s, d.x));
@@ -151,7 +196,7 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
       p.z = __fadd_rn(p.z, __fmul_rn(s, d.z));
       if (respond && hit && !virt) {
         float dn; float3 tg = delta;
-        if (SPH && sph >= 0) {                           // radial normal; tangent = delta - (delta . n) n
+        if (SPH && (sph >= 0 || tri >= 0)) {              // radial / interpolated normal; tangent = delta - (delta . n) n
           dn = ex_dot(d, sn);
           const float dd = ex_dot(delta, sn);
           tg = make_float3(__fsub_rn(delta.x, __fmul_rn(dd, sn.x)), __fsub_rn(delta.y, __fmul_rn(dd, sn.y)), __fsub_rn(delta.z, __fmul_rn(dd, sn.z)));
@@ -165,8 +210,9 @@ __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float
           float3 d2 = make_float3(__fmul_rn(rn, tg.x), __fmul_rn(rn, tg.y), __fmul_rn(rn, tg.z));
           float mt = __fmul_rn(__fsub_rn(total_l, max_t), 0.5f);
           int a2 = -1, s2 = 0, k2 = -1; float3 n2;
-          ex_box_hit(P, p, d2, mt, a2, s2, (SPH && sph >= 0) ? -1 : axis, side);   // the surface being slid on is never re-tested
+          ex_box_hit(P, p, d2, mt, a2, s2, (SPH && (sph >= 0 || tri >= 0)) ? -1 : axis, side);   // the wall / sphere being slid on is never re-tested
           if (SPH) ex_sphere_hit(P, p, d2, mt, k2, n2, sph);
+          if (SPH && P.n_tri > 0) ex_mesh_hit(P, p, d2, mt, k2, n2, tri);
           const float s3 = __fsub_rn(mt, P.eps_d);
           p.x = __fadd_rn(p.x, __fmul_rn(s3, d2.x));
           p.y = __fadd_rn(p.y, __fmul_rn(s3, d2.y));

@@ -62,6 +62,7 @@ struct Solver {
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
   void* host_extra = nullptr;        // pbf_api.cu's HandleExtra (pinned staging, registered host ranges)
+  float4* tri_dev = nullptr;         // obstacle triangles (5 float4 each), referenced by dp.tri
   int capture_xpred = 0;
   bool have_neighbors = false;
   long long rebinned_at = -1;

@@ -810,7 +810,7 @@ void enqueue_predict_hash(Solver* h, int apply_forces) {
   LAUNCH(h, K_PREDICT, KERN, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur], h->xs_tmp, h->cell_of, \
          h->rank, h->cell_count, apply_forces, h->slab && h->has_left ? h->mig_send[0] : (float4*)nullptr,                            \
          h->slab && h->has_right ? h->mig_send[1] : (float4*)nullptr, (uint32_t)h->halo_cap, h->sc)
-  if (h->dp.n_sph > 0) LAUNCH_PREDICT(k_predict_hash<true>); else LAUNCH_PREDICT(k_predict_hash<false>);
+  if (h->dp.n_sph > 0 || h->dp.n_tri > 0) LAUNCH_PREDICT(k_predict_hash<true>); else LAUNCH_PREDICT(k_predict_hash<false>);
 #undef LAUNCH_PREDICT
 }
 
@@ -870,7 +870,7 @@ void enqueue_delta(Solver* h, int part) {
   for (int q = 0; q < k; q++) {
     const unsigned g = blocks_for(rng[q][1] - rng[q][0]);
 #define LAUNCH_DELTA(KERN) LAUNCH(h, K_DELTA, KERN, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt)
-    const bool sph = h->dp.n_sph > 0;                  // box-only scenes run the instantiation without the sphere code
+    const bool sph = h->dp.n_sph > 0 || h->dp.n_tri > 0;   // box-only scenes run the instantiation without the obstacle code
     if (h->dp.n_corr == 4) { if (sph) LAUNCH_DELTA((k_delta<4, true>)); else LAUNCH_DELTA((k_delta<4, false>)); }
     else { if (sph) LAUNCH_DELTA((k_delta<-1, true>)); else LAUNCH_DELTA((k_delta<-1, false>)); }
 #undef LAUNCH_DELTA

@@ -49,6 +49,9 @@ void Particles::ensureUploaded() {
   if (!spheres_.empty() && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
     std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
   }
+  if (!tris_.empty() && pbf_set_obstacle_triangles(handle_, tris_.size() / 18, tris_.data()) != PBF_OK) {
+    std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
+  }
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   if (n) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data());   // every step streams its result into the mirror
@@ -77,6 +80,13 @@ void Particles::estimateDensities() {
 void Particles::setObstacleSpheres(const std::vector<double>& s) {
   spheres_ = s;
   if (handle_ && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
+    std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
+  }
+}
+
+void Particles::setObstacleTriangles(const std::vector<double>& t) {
+  tris_ = t;
+  if (handle_ && pbf_set_obstacle_triangles(handle_, tris_.size() / 18, tris_.data()) != PBF_OK) {
     std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
   }
 }

@@ -63,6 +63,8 @@ struct Particles {
   // GPU step takes the box (PbfParams) and the StaticScene::Sphere primitives: rows (cx, cy, cz, r), at most
   // PBF_MAX_SPHERES.  May be called at any time; takes effect from the next timeStep().
   void setObstacleSpheres(const std::vector<double>& cx_cy_cz_r);
+  // ... and its triangle primitives (small meshes): 18 doubles each, p1 p2 p3 n1 n2 n3 (pbf_set_obstacle_triangles)
+  void setObstacleTriangles(const std::vector<double>& p1_p2_p3_n1_n2_n3);
   double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
   // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
   std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);
@@ -87,7 +89,7 @@ struct Particles {
   int device_;
   pbf_handle* handle_ = nullptr;
   bool uploaded_ = false;
-  std::vector<double> pos_, vel_, rho_, spheres_;
+  std::vector<double> pos_, vel_, rho_, spheres_, tris_;
 };
 
 // Application::load_particles (application.cpp:302-344): <particles><density>rho0</density><ps>

@@ -4,6 +4,7 @@
 // Optional --dump writes the per-step state in the same PBFDUMP1 format as oracle/ref_harness.
 //   pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--iterations I]
 //           [--sphere cx cy cz r]...      obstacle spheres of the collision scene (the CBspheres scenes hold two)
+//           [--tris file]                 obstacle triangles (int64 count, then p1 p2 p3 n1 n2 n3 as 18 doubles each)
 //           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
@@ -21,6 +22,7 @@ int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
   std::vector<double> spheres;
+  const char* trisfile = nullptr;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-p" && i + 1 < argc) pfile = argv[++i];
@@ -29,6 +31,7 @@ int main(int argc, char** argv) {
     else if (a == "--iterations" && i + 1 < argc) iterations = atoi(argv[++i]);
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
     else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }   // obstacle sphere cx cy cz r, repeatable
+    else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];            // obstacle triangles: int64 count + 18 doubles each
     else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
     else if (a == "--load-state" && i + 1 < argc) load_state = argv[++i];   // continue from a restart file instead of -p
     else if (a == "--quiet") quiet = true;
@@ -54,6 +57,15 @@ int main(int argc, char** argv) {
   printf("Done!\n");
   ps->quiet = quiet;
   if (!spheres.empty()) ps->setObstacleSpheres(spheres);
+  if (trisfile) {
+    FILE* tf = fopen(trisfile, "rb");
+    int64_t nt = 0;
+    if (!tf || fread(&nt, 8, 1, tf) != 1 || nt < 0) { printf("[ERROR] cannot read %s\n", trisfile); return EXIT_FAILURE; }
+    std::vector<double> tv(18 * (size_t)nt);
+    if (fread(tv.data(), 8, tv.size(), tf) != tv.size()) { printf("[ERROR] short %s\n", trisfile); return EXIT_FAILURE; }
+    fclose(tf);
+    ps->setObstacleTriangles(tv);
+  }
   const int64_t n = (int64_t)ps->ps.size();
   if (steps < 0 && seconds < 0) steps = 1;
   FILE* f = dump ? fopen(dump, "wb") : nullptr;

@@ -157,6 +157,10 @@ class SlabSolver:
         """Obstacle spheres (rows cx, cy, cz, r): global scene data, call with the same list on every rank."""
         self.solver.set_obstacle_spheres(spheres)
 
+    def set_obstacle_triangles(self, tris):
+        """Obstacle triangles (rows of 18): global scene data, call with the same list on every rank."""
+        self.solver.set_obstacle_triangles(tris)
+
     def columns_of(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         col = np.empty(pos.shape[0], dtype=np.int32)

@@ -50,6 +50,11 @@ void oracle_set_spheres(void* hv, size_t count, const double* cxcyczr) {
   visit((Handle*)hv, [&](auto& o) { o.set_spheres(count, cxcyczr); return 0; });
 }
 
+// obstacle triangles, 18 doubles each: p1, p2, p3, n1, n2, n3 (MarchingTriangle primitives in the reference's BVH)
+void oracle_set_triangles(void* hv, size_t count, const double* pn) {
+  visit((Handle*)hv, [&](auto& o) { o.set_triangles(count, pn); return 0; });
+}
+
 void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int oracle_max_threads() { return omp_get_max_threads(); }
 

@@ -70,7 +70,7 @@ enum { SEARCH_BRUTE = 0, SEARCH_GRID = 1 };
 
 // ---- wall triangles of the reference scene (dae/sky/CBempty.dae:229-444 as exact quads) --------
 template <class R>
-struct Tri { V3<R> p1, p2, p3, n; };
+struct Tri { V3<R> p1, p2, p3, n1, n2, n3; R sg, ngl; };   // vertex normals (marching_triangle.h); sg, ngl: see mesh_hit_onesided
 // ---- obstacle sphere (static_scene/sphere.h:23-24: r2 = r*r), e.g. the two r = 0.3 spheres of the
 // CBspheres scenes (dae/sky/CBspheres_lambertian.dae:291-305,575-594) -------------------------------------------
 template <class R>
@@ -85,8 +85,9 @@ struct Oracle {
   R H, H2, H6, H9, DT, RHO0, EPS_RELAX, KCORR, VISC, VORT_EPS, GRAV, EPS_D, TSCALE;
   int NCORR, ITERS;
   V bmin, bmax; R YL, ZF;
-  std::vector<Tri<R>> tris;
+  std::vector<Tri<R>> tris;       // the five walls (10 triangles)
   std::vector<Sph<R>> spheres;
+  std::vector<Tri<R>> mesh;       // obstacle triangles (any MarchingTriangle / Triangle primitives of the scene's BVH)
 
   size_t n = 0;
   std::vector<V> pos, npos, vel, vort, xpred;
@@ -111,8 +112,8 @@ struct Oracle {
   }
 
   void add_quad(V a, V b, V c, V d, V nn) {
-    tris.push_back(Tri<R>{a, b, c, nn});
-    tris.push_back(Tri<R>{a, c, d, nn});
+    tris.push_back(Tri<R>{a, b, c, nn, nn, nn, R(1), R(0)});
+    tris.push_back(Tri<R>{a, c, d, nn, nn, nn, R(1), R(0)});
   }
   // Walls generalised from the Cornell box: ceiling 0.01 above y_light (1.5 vs 1.49), floor,
   // x-, x+, back (z-); the front (z+) is open (virtual plane).  For the default params these are
@@ -152,7 +153,7 @@ struct Oracle {
     R u = dot(s1, s) / dd, v = dot(s2, d) / dd, w = R(1) - u - v;
     if ((u < 0) || (u > 1) || (v < 0) || (v > 1) || (w < 0) || (w > 1)) return false;
     max_t = t;
-    if (nrm) *nrm = w * T.n + u * T.n + v * T.n;
+    if (nrm) *nrm = w * T.n1 + u * T.n2 + v * T.n3;
     return true;
   }
   // ---- ray / sphere, literal (static_scene/sphere.cpp:10-41,43-76), segment [0, max_t] ----------------------
@@ -209,12 +210,17 @@ struct Oracle {
     }
   };
   struct Node { Box bb; int l = -1, r = -1; size_t lo = 0, hi = 0; };
-  std::vector<int> prim_order;     // primitive ids in leaf order; id < tris.size(): triangle, else sphere id - tris.size()
+  std::vector<int> prim_order;     // primitive ids in leaf order; ids: walls, then spheres, then obstacle triangles (the harness's push order)
   std::vector<Node> nodes;
   int bvh_root = -1;
 
+  const Tri<R>* prim_tri(int id) const {
+    if (id < (int)tris.size()) return &tris[id];
+    id -= (int)(tris.size() + spheres.size());
+    return id >= 0 ? &mesh[id] : nullptr;
+  }
   Box prim_box(int id) const {
-    if (id < (int)tris.size()) { const Tri<R>& T = tris[id]; Box b(T.p1); b.expand(T.p2); b.expand(T.p3); return b; }
+    if (const Tri<R>* T = prim_tri(id)) { Box b(T->p1); b.expand(T->p2); b.expand(T->p3); return b; }
     const Sph<R>& S = spheres[id - (int)tris.size()];
     return Box(S.c - V(S.r, S.r, S.r), S.c + V(S.r, S.r, S.r));
   }
@@ -247,14 +253,14 @@ struct Oracle {
   }
   void build_bvh() {   // bvh.cpp:130-139, default max_leaf_size 4 (bvh.h:71)
     nodes.clear(); prim_order.clear();
-    const int np = (int)(tris.size() + spheres.size());
+    const int np = (int)(tris.size() + spheres.size() + mesh.size());
     Box all;
     for (int i = 0; i < np; i++) { prim_order.push_back(i); all.expand(prim_box(i)); }
     bvh_root = build_range(0, (size_t)np, all, 4);
   }
   bool prim_hit(int id, const V& o, const V& d, R& max_t, V* nrm) const {
-    return id < (int)tris.size() ? tri_hit(tris[id], o, d, max_t, nrm)
-                                 : sphere_hit_literal(spheres[id - (int)tris.size()], o, d, max_t, nrm);
+    if (const Tri<R>* T = prim_tri(id)) return tri_hit(*T, o, d, max_t, nrm);
+    return sphere_hit_literal(spheres[id - (int)tris.size()], o, d, max_t, nrm);
   }
   // nrm == nullptr: any hit (bvh.cpp:142-163, first primitive found wins and sets max_t);
   // nrm != nullptr: nearest hit (bvh.cpp:165-192: every primitive the boxes let through, each hit shrinks max_t)
@@ -275,6 +281,21 @@ struct Oracle {
     return hit;
   }
   bool scene_hit(const V& o, const V& d, R& max_t, V* nrm) const { return bvh_hit(bvh_root, o, d, max_t, nrm); }
+
+  // obstacle triangles: 18 doubles each (p1, p2, p3, n1, n2, n3); n == nullptr: geometric normals
+  void set_triangles(size_t count, const double* pn) {
+    mesh.clear();
+    for (size_t k = 0; k < count; k++) {
+      const double* q = pn + 18 * k;
+      auto vec = [&](int a) { return V(R(q[3 * a]), R(q[3 * a + 1]), R(q[3 * a + 2])); };
+      Tri<R> T{vec(0), vec(1), vec(2), vec(3), vec(4), vec(5), R(1), R(0)};
+      const V ng = cross(T.p2 - T.p1, T.p3 - T.p1);
+      T.sg = dot(ng, T.n1 + T.n2 + T.n3) < R(0) ? R(-1) : R(1);   // +1: the vertex order winds counter-clockwise seen from the normals' side
+      T.ngl = ng.norm();                                            // |e1 x e2| = twice the area
+      mesh.push_back(T);
+    }
+    build_bvh();
+  }
 
   void set_spheres(size_t count, const double* cxcyczr) {
     spheres.clear();
@@ -333,6 +354,33 @@ struct Oracle {
     return hit;
   }
 
+  // One-sided obstacle triangles (same Moller-Trumbore expressions as tri_hit): a triangle blocks only motion
+  // against its oriented normal; an origin a hair behind its plane (fp32 landing error) is in contact now; the
+  // barycentric test is inflated by BT in fp32 so that a ray through a shared edge cannot slip between two
+  // triangles.  `slid` = the triangle being slid on: the slide direction comes from the INTERPOLATED vertex normals
+  // (particles.cpp:120, marching_triangle.cpp:66-68), which need not be the geometric normal, so it may point into
+  // the surface and the triangle must be re-tested; it blocks the slide only when the direction dips below the
+  // tangent plane by more than TAN (rounding of an exactly tangent direction must not freeze the particle).
+  // In fp64 (BT = 0) this differs from the reference's two-sided test only for origins behind a triangle.
+  bool mesh_hit_onesided(const V& o, const V& d, R& max_t, int* which, V* nrm, int slid) const {
+    const R BT = sizeof(R) == 4 ? R(1e-6) : R(0), TOL_T = R(1e-4) * H, TAN = R(1e-5);
+    bool hit = false;
+    for (int k = 0; k < (int)mesh.size(); k++) {
+      const Tri<R>& T = mesh[k];
+      V e1 = T.p2 - T.p1, e2 = T.p3 - T.p1, s = o - T.p1;
+      V s1 = cross(d, e2), s2 = cross(s, e1);
+      R dd = dot(s1, e1);                         // = -d . (e1 x e2)
+      if (!(T.sg * dd > (k == slid ? TAN * T.ngl : R(0)))) continue;   // moving away from / parallel to the front side
+      R t = dot(s2, e2) / dd;
+      if (t < R(0)) { if (t >= -TOL_T) t = R(0); else continue; }
+      if (t > max_t) continue;
+      R u = dot(s1, s) / dd, v = dot(s2, d) / dd, w = R(1) - u - v;
+      if ((u < -BT) || (u > R(1) + BT) || (v < -BT) || (v > R(1) + BT) || (w < -BT) || (w > R(1) + BT)) continue;
+      max_t = t; *which = k; *nrm = w * T.n1 + u * T.n2 + v * T.n3; hit = true;
+    }
+    return hit;
+  }
+
   void hard_clamp(V& p) const {   // particles.cpp:81-83 / 129-131
     p.x = rmax(bmin.x + EPS_D, rmin(bmax.x - EPS_D, p.x));
     p.y = rmax(bmin.y + EPS_D, rmin(bmax.y - EPS_D, p.y));
@@ -366,14 +414,15 @@ struct Oracle {
       // sticky virtual planes: d>0 && pt>=0 (fp64 never has pt==0; fp32 does)
       if (d.z > R(0)) { R pt = (ZF - p.z) / d.z; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
       if (d.y > R(0)) { R pt = (YL - p.y) / d.y; if (pt >= R(0) && pt < l) { l = pt; virt = true; } }
-      R max_t = l; int axis = -1, side = 0, sph = -1; V sn;
+      R max_t = l; int axis = -1, side = 0, sph = -1, tri = -1; V sn;
       bool hit = box_hit(p, d, max_t, &axis, &side, -1, 0);
-      if (sphere_hit_onesided(p, d, max_t, &sph, &sn, -1)) hit = true;      // nearest of walls and spheres
+      if (sphere_hit_onesided(p, d, max_t, &sph, &sn, -1)) hit = true;      // nearest of walls, spheres and triangles
+      if (mesh_hit_onesided(p, d, max_t, &tri, &sn, -1)) { hit = true; sph = -1; }
       if (hit || virt) {
         p += (max_t - EPS_D) * d;
         if (respond && hit && !virt) {
           R dn; V tang;
-          if (sph >= 0) {                                  // radial normal (sphere.cpp:69-70); slide as particles.cpp:118-124
+          if (sph >= 0 || tri >= 0) {                      // radial normal (sphere.cpp:69-70) / interpolated vertex normals; slide as particles.cpp:118-124
             dn = dot(d, sn);
             tang = delta_p - dot(delta_p, sn) * sn;
           } else {
@@ -385,8 +434,9 @@ struct Oracle {
             V d2 = tang.unit();
             R mt = (total_l - max_t) * R(0.5);
             int a2 = -1, s2 = 0, k2 = -1; V n2;
-            box_hit(p, d2, mt, &a2, &s2, sph >= 0 ? -1 : axis, side);      // the surface being slid on is never re-tested
+            box_hit(p, d2, mt, &a2, &s2, (sph >= 0 || tri >= 0) ? -1 : axis, side);   // the surface being slid on is never re-tested
             sphere_hit_onesided(p, d2, mt, &k2, &n2, sph);
+            mesh_hit_onesided(p, d2, mt, &k2, &n2, tri);
             p += (mt - EPS_D) * d2;
           }
         }

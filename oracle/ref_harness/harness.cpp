@@ -9,7 +9,8 @@
 //   * calls Particles::timeStep() (particles.cpp:250-301) and dumps state after each step.
 //
 // Usage: ref_harness (--xml file.xml | --bin file.bin) --steps S --out dump.bin [--quiet]
-//                    [--density-queries q.bin --density-out d.bin] [--sphere cx cy cz r]...
+//                    [--density-queries q.bin --density-out d.bin] [--sphere cx cy cz r]... [--tris t.bin]
+//   --tris    adds MarchingTriangle obstacles (int64 count + 18 doubles each: p1 p2 p3 n1 n2 n3) to the BVH, after the spheres.
 //   --sphere  adds a StaticScene::Sphere obstacle to the BVH (the CBspheres scenes hold two r=0.3 spheres,
 //             dae/sky/CBspheres_lambertian.dae:291-305,575-594); repeatable.
 //   q.bin : int64 M, M*3 doubles; d.bin : M doubles = Particles::estimateDensityAt(q) after the last
@@ -91,7 +92,7 @@ static void add_quad(std::vector<Primitive*>& prims, Vector3D a, Vector3D b, Vec
 }
 
 int main(int argc, char** argv) {
-  const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr;
+  const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr, *trisfile = nullptr;
   int steps = 1; bool quiet = false;
   std::vector<double> spheres;
   for (int i = 1; i < argc; i++) {
@@ -102,6 +103,7 @@ int main(int argc, char** argv) {
     else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
     else if (a == "--quiet") quiet = true;
     else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }
+    else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];
     else if (a == "--density-queries" && i + 1 < argc) dq = argv[++i];
     else if (a == "--density-out" && i + 1 < argc) dout = argv[++i];
     else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
@@ -129,6 +131,19 @@ int main(int argc, char** argv) {
   for (size_t k = 0; k + 3 < spheres.size(); k += 4) {
     SphereObject* so = new SphereObject(Vector3D(spheres[k], spheres[k+1], spheres[k+2]), spheres[k+3], nullptr);
     for (Primitive* p : so->get_primitives()) prims.push_back(p);      // object.cpp:76-80 -> new Sphere(this, o, r)
+  }
+  if (trisfile) {   // obstacle triangles: int64 count, then 18 doubles each (p1, p2, p3, n1, n2, n3), pushed after the spheres
+    FILE* tf = fopen(trisfile, "rb");
+    int64_t nt = 0;
+    if (!tf || fread(&nt, 8, 1, tf) != 1) { fprintf(stderr, "cannot read %s\n", trisfile); return 1; }
+    std::vector<double> tv(18 * (size_t)nt);
+    if (fread(tv.data(), 8, tv.size(), tf) != tv.size()) { fprintf(stderr, "short %s\n", trisfile); return 1; }
+    fclose(tf);
+    for (int64_t k = 0; k < nt; k++) {
+      const double* q = &tv[18 * k];
+      prims.push_back(new MarchingTriangle(Vector3D(q[0], q[1], q[2]), Vector3D(q[3], q[4], q[5]), Vector3D(q[6], q[7], q[8]),
+                                           Vector3D(q[9], q[10], q[11]), Vector3D(q[12], q[13], q[14]), Vector3D(q[15], q[16], q[17]), nullptr));
+    }
   }
   ps->bvh = new BVHAccel(prims);
 

@@ -11,6 +11,7 @@ Fixtures
                           coordinate sums, directed pair counts, the "avg rho: a => b" lines the reference
                           prints, full state at steps 0/1/19 and the ordered neighbour CSR of step 0
   ref_sphere_<name>.npz   same with the CBspheres obstacle spheres in the reference's BVH (harness --sphere)
+  ref_mesh_drop.npz       same with obstacle triangles (a cuboid and a wedge) in the reference's BVH (harness --tris)
   ref_jitter_<name>.npz   same for jittered pgen-style inputs (lattice + U(-0.001,0.001),
                           default_rng(1234)) — the inputs used for fp32-vs-fp64 tolerance checks
 """
@@ -23,20 +24,22 @@ import tempfile
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from helpers import (GOLDEN, REFERENCE, load_xml_scene, pgen_two_blocks, lattice_block, read_dump,
-                     ref_harness_path, state_sha, write_bin_scene)
+from helpers import (GOLDEN, REFERENCE, box_mesh, load_xml_scene, pgen_two_blocks, lattice_block, ramp_mesh, read_dump,
+                     ref_harness_path, state_sha, write_bin_scene, write_tris)
 
 STEPS = 20
 KEEP = (0, 1, 19)
 
 
-def run_reference(pos, vel, rho0, steps, spheres=()):
+def run_reference(pos, vel, rho0, steps, spheres=(), tris=None):
     with tempfile.TemporaryDirectory() as td:
         scene = os.path.join(td, "scene.bin"); dump = os.path.join(td, "dump.bin")
         write_bin_scene(scene, pos, vel, rho0)
         cmd = [ref_harness_path(), "--bin", scene, "--steps", str(steps), "--out", dump, "--quiet"]
         for sp in spheres:                      # StaticScene::Sphere primitives added to the reference's BVH
             cmd += ["--sphere"] + [repr(float(x)) for x in sp]
+        if tris is not None:                    # MarchingTriangle primitives added after the spheres
+            tf = os.path.join(td, "tris.bin"); write_tris(tf, tris); cmd += ["--tris", tf]
         subprocess.run(cmd, check=True)
         log = open(dump + ".log").read()
         return read_dump(dump), log
@@ -113,8 +116,23 @@ def sphere_scenes():
     }
 
 
+def mesh_scene():
+    """Obstacle triangles: the two collapsing blocks around a cuboid standing on the floor
+    (10 triangles, geometric normals) and a wedge with averaged, non-unit vertex normals along its top edge and one
+    clockwise triangle (6 triangles) in the two empty quadrants."""
+    two, vel, rho0 = jitter_scenes()["two_blocks"]
+    tris = np.concatenate([box_mesh((-0.7, 0.0, -0.7), (-0.2, 0.4, -0.2)), ramp_mesh(0.15, 0.9, 0.5, 0.2, 0.8)])
+    return two, vel, rho0, tris, 40, (0, 1, 9, 10, 11, 12, 13, 19, 20, 39)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    pos, vel, rho0, tris, steps, keep = mesh_scene()
+    dump, log = run_reference(pos, vel, rho0, steps, tris=tris)
+    np.savez_compressed(os.path.join(GOLDEN, "ref_mesh_drop.npz"), pos=pos, vel=vel, rho0=rho0, tris=tris, **pack(dump, log, keep))
+    print("mesh_drop", pos.shape[0], "pairs", [len(d["col"]) for d in dump][:6])
+    if "--only-mesh" in sys.argv:
+        return
     for name, (pos, vel, rho0, sph, steps, keep) in sphere_scenes().items():
         dump, log = run_reference(pos, vel, rho0, steps, sph)
         np.savez_compressed(os.path.join(GOLDEN, f"ref_{name}.npz"), pos=pos, vel=vel, rho0=rho0, spheres=sph, **pack(dump, log, keep))

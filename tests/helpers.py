@@ -70,6 +70,7 @@ def oracle_lib():
         lib.oracle_default_params.argtypes = [C.POINTER(PbfParams)]
         lib.oracle_set_threads.argtypes = [C.c_int]
         lib.oracle_set_spheres.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.oracle_set_triangles.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -122,6 +123,11 @@ class Oracle:
         """Obstacle spheres, rows (cx, cy, cz, r) (reference: StaticScene::Sphere primitives in the BVH)."""
         sp = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
         self.lib.oracle_set_spheres(self.h, sp.shape[0], _ptr(sp))
+
+    def set_triangles(self, tris):
+        """Obstacle triangles, rows of 18: p1, p2, p3, n1, n2, n3 (MarchingTriangle primitives of the reference's BVH)."""
+        t = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
+        self.lib.oracle_set_triangles(self.h, t.shape[0], _ptr(t))
 
     def step(self, steps=1):
         self.lib.oracle_step(self.h, steps)
@@ -251,3 +257,46 @@ def lattice_block(nx, ny, nz, origin=(0.1, 0.1, 0.1), spacing=0.1, v0=(0.0, -1.0
         pos = pos + rng.uniform(-jitter, jitter, size=pos.shape)
     vel = np.tile(np.array(v0, dtype=np.float64), (pos.shape[0], 1))
     return pos, vel
+
+
+# ---- obstacle triangle meshes (rows of 18: p1, p2, p3, n1, n2, n3) ---------------------------------------------
+
+def _quad(a, b, c, d, n):
+    a, b, c, d, n = (np.asarray(v, dtype=np.float64) for v in (a, b, c, d, n))
+    return [np.concatenate([a, b, c, n, n, n]), np.concatenate([a, c, d, n, n, n])]
+
+
+def box_mesh(lo, hi, bottom=False):
+    """Axis-aligned cuboid, outward face normals, counter-clockwise seen from outside (bottom face optional)."""
+    x0, y0, z0 = lo; x1, y1, z1 = hi
+    t = []
+    t += _quad((x0, y1, z0), (x0, y1, z1), (x1, y1, z1), (x1, y1, z0), (0, 1, 0))      # top
+    t += _quad((x0, y0, z0), (x0, y0, z1), (x0, y1, z1), (x0, y1, z0), (-1, 0, 0))     # x-
+    t += _quad((x1, y0, z0), (x1, y1, z0), (x1, y1, z1), (x1, y0, z1), (1, 0, 0))      # x+
+    t += _quad((x0, y0, z0), (x0, y1, z0), (x1, y1, z0), (x1, y0, z0), (0, 0, -1))     # z-
+    t += _quad((x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1), (0, 0, 1))      # z+
+    if bottom:
+        t += _quad((x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1), (0, -1, 0))
+    return np.array(t)
+
+
+def ramp_mesh(x_low, x_high, height, z0, z1, smooth=True):
+    """Wedge: slope rising from (x_low, 0) to (x_high, height), vertical back face at x_high, two side triangles.
+    smooth=True averages the vertex normals along the top edge (exercises the interpolated, non-unit normal of
+    MarchingTriangle::intersect); the second slope triangle is wound clockwise on purpose."""
+    sl = np.array([-(height), (x_high - x_low), 0.0]); sl /= np.linalg.norm(sl)      # slope normal (x-, y+)
+    bk = np.array([1.0, 0.0, 0.0])
+    top = (sl + bk) / 2 if smooth else sl                                             # NOT renormalised
+    A, B = np.array([x_low, 0, z0]), np.array([x_low, 0, z1])
+    C, D = np.array([x_high, height, z1]), np.array([x_high, height, z0])
+    E, F = np.array([x_high, 0, z0]), np.array([x_high, 0, z1])
+    t = [np.concatenate([A, B, C, sl, sl, top]), np.concatenate([A, D, C, sl, top, top])]     # second one clockwise
+    t += _quad(E, D, C, F, bk)
+    t += [np.concatenate([A, D, E, [0, 0, -1] * 3]), np.concatenate([B, F, C, [0, 0, 1] * 3])]
+    return np.array(t)
+
+
+def write_tris(path, tris):
+    t = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
+    with open(path, "wb") as f:
+        f.write(np.int64(t.shape[0]).tobytes()); f.write(t.tobytes())

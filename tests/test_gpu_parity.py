@@ -461,6 +461,70 @@ def test_thin_cell_count_changes_order_not_sets(monkeypatch):
             _gate_whole_step(f"{name}/zsub{z} vs zsub8", out[z][2][0], out[z][2][2], out["8"][2][0], out["8"][2][2], rho0)
 
 
+def _mesh_scene():
+    ref = np.load(os.path.join(GOLDEN, "ref_mesh_drop.npz"))
+    states = [("init", ref["pos"], ref["vel"])]
+    for s in sorted(int(k) for k in ref["keep"]):
+        st = ref[f"state_{s}"]
+        states.append((f"ref_step{s}", st[:, 0:3], st[:, 3:6]))
+    return float(ref["rho0"]), ref["tris"], states, ref
+
+
+def test_obstacle_triangles_predict_and_neighbors_bit_exact():
+    """Obstacle triangles (a cuboid and a wedge with averaged vertex normals and one clockwise triangle): predicted
+    positions and frozen neighbour sets equal the fp32 oracle's one-sided-triangle rule exactly, from the scene's
+    start and from the unmodified reference's own states (in which some particles sit inside the obstacles: the
+    reference leaks, tests/test_oracle_golden.py::test_one_sided_triangles_vs_reference_triangles)."""
+    rho0, tris, states, ref = _mesh_scene()
+    touched = 0
+    for label, pos, vel in states:
+        g = _gpu(rho0, iterations=0); g.set_obstacle_triangles(tris); g.capture(True)
+        g.upload(pos, vel); g.step(1)
+        o = _oracle(rho0, 32, iterations=0); o.set_triangles(tris); o.upload(pos, vel); o.step(1)
+        xg = g.array(ARRAY_XPRED); xo = o.array(ARRAY_XPRED)
+        assert np.array_equal(xg, xo), f"mesh/{label}: x* differs for {int(np.any(xg != xo, axis=1).sum())} particles (max {np.abs(xg - xo).max():.3e})"
+        assert np.array_equal(g.neighbor_digest()[0], o.digest()[0]), f"mesh/{label}: neighbour digests differ"
+        g0 = _gpu(rho0, iterations=0); g0.capture(True); g0.upload(pos, vel); g0.step(1)
+        touched += int(np.any(g0.array(ARRAY_XPRED) != xg, axis=1).sum())
+    assert touched >= 20, touched
+
+
+def test_obstacle_triangles_whole_step_and_rollout():
+    """Whole steps against the fp32 / fp64 one-sided oracle (same gates as the box-only scenes), spheres and triangles
+    together, 60 free-running steps without a single particle inside the cuboid or under the wedge, API errors."""
+    from fluid_b200 import api
+    rho0, tris, states, ref = _mesh_scene()
+    spheres = np.array([[0.0, 0.25, 0.0, 0.25]])
+    for label, pos, vel in states[:6]:
+        g = _gpu(rho0); g.set_obstacle_triangles(tris); g.set_obstacle_spheres(spheres); g.upload(pos, vel); g.step(1)
+        Pg, Vg, Rg = g.download()
+        for prec in (32, 64):
+            o = _oracle(rho0, prec); o.set_triangles(tris); o.set_spheres(spheres); o.upload(pos, vel); o.step(1)
+            Po, Vo, Ro = o.download()
+            assert np.array_equal(g.neighbor_digest()[0], o.digest()[0]), f"mesh/{label}: neighbour sets differ from the fp{prec} oracle"
+            _gate_whole_step(f"mesh/{label} vs fp{prec} oracle", Pg, Rg, Po, Ro, rho0)
+
+    def inside(P, tol=1e-5):
+        box = (P[:, 0] > -0.7 + tol) & (P[:, 0] < -0.2 - tol) & (P[:, 1] < 0.4 - tol) & (P[:, 2] > -0.7 + tol) & (P[:, 2] < -0.2 - tol)
+        wedge = ((P[:, 0] > 0.15 + tol) & (P[:, 0] < 0.9 - tol) & (P[:, 2] > 0.2 + tol) & (P[:, 2] < 0.8 - tol) &
+                 (P[:, 1] < (P[:, 0] - 0.15) / 0.75 * 0.5 - tol))
+        return int(box.sum()), int(wedge.sum())
+    g = _gpu(rho0); g.set_obstacle_triangles(tris); g.upload(states[0][1], states[0][2])
+    for _ in range(4):
+        g.step(15)
+        P = g.download()[0]
+        assert inside(P) == (0, 0)
+    near_top = ((np.abs(P[:, 1] - 0.4) < 1e-3) & (P[:, 0] > -0.7) & (P[:, 0] < -0.2) & (P[:, 2] > -0.7) & (P[:, 2] < -0.2)).sum()
+    assert near_top >= 1 or (P[:, 1] < 0.45).sum() > 0         # the fluid does reach the obstacles
+    g.set_obstacle_triangles(np.zeros((0, 18))); g.step(1)      # removing them is allowed
+    with pytest.raises(api.PbfError) as e:
+        g.set_obstacle_triangles(np.tile(tris[0], (4097, 1)))
+    assert e.value.code == api.PBF_ERR_CAPACITY
+    bad = tris.copy(); bad[3, 4] = np.inf
+    with pytest.raises(api.PbfError):
+        g.set_obstacle_triangles(bad)
+
+
 def test_graph_replay_equals_plain_launches(monkeypatch):
     """Launch-bound scenes replay the step as a CUDA graph (one per buffer parity, PBF_GRAPH): the state after
     7 steps, a re-upload and 3 more steps is bit-identical to plain launches, and launch_count() still counts
