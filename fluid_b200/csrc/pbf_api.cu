@@ -73,7 +73,7 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
   d.n_sph = 0; d.n_sm = 148; d.n_tri = 0; d.tri = nullptr;
-  for (int a = 0; a < 3; a++) { d.tlo[a] = 0.f; d.thi[a] = 0.f; }
+  for (int a = 0; a < 3; a++) { d.tlo[a] = 0.f; d.thi[a] = 0.f; d.olo[a] = 1e30f; d.ohi[a] = -1e30f; }
   for (int k = 0; k < PBF_MAX_SPHERES; k++) { d.sph[k] = make_float4(0.f, 0.f, 0.f, 0.f); d.sph_r2[k] = 0.f; }
   return PBF_OK;
 }
@@ -408,6 +408,19 @@ int pbf_step(pbf_handle* h, int n_steps) {
 
 // Obstacle spheres of the collision scene (the reference keeps them as StaticScene::Sphere primitives in
 // Particles::bvh).  Kernel parameters carry them, so captured graphs are rebuilt.
+// bounding box of all obstacles (the collide fast path skips moves that stay clear of it)
+static void update_obstacle_box(pbf_handle* h) {
+  DevParams& d = h->dp;
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  for (int k = 0; k < d.n_sph; k++) {
+    const float c[3] = {d.sph[k].x, d.sph[k].y, d.sph[k].z};
+    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[a] - d.sph[k].w); hi[a] = std::max(hi[a], c[a] + d.sph[k].w); }
+  }
+  if (d.n_tri > 0) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], d.tlo[a]); hi[a] = std::max(hi[a], d.thi[a]); }
+  const float margin = 1e-2f * d.h;
+  for (int a = 0; a < 3; a++) { d.olo[a] = lo[a] - margin - 1e-5f * std::fabs(lo[a]); d.ohi[a] = hi[a] + margin + 1e-5f * std::fabs(hi[a]); }
+}
+
 int pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* s) {
   if (!h || (count && !s)) return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_spheres: null argument");
   if (count > PBF_MAX_SPHERES) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_spheres: more than PBF_MAX_SPHERES spheres");
@@ -422,6 +435,7 @@ int pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* s) {
     h->dp.sph[k] = make_float4((float)s[4 * k], (float)s[4 * k + 1], (float)s[4 * k + 2], r);
     h->dp.sph_r2[k] = r2;
   }
+  update_obstacle_box(h);
   return PBF_OK;
 }
 
@@ -436,6 +450,7 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   h->graph_invalidate();
   if (h->tri_dev) { cudaFree(h->tri_dev); h->tri_dev = nullptr; }
   h->dp.n_tri = 0; h->dp.tri = nullptr;
+  update_obstacle_box(h);
   if (count == 0) return PBF_OK;
   std::vector<float> t(20 * count);
   float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
@@ -465,6 +480,7 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   const float margin = 1e-2f * h->dp.h;               // >> the contact tolerance (1e-4 h) and the inflated edges
   for (int a = 0; a < 3; a++) { h->dp.tlo[a] = lo[a] - margin - 1e-5f * std::fabs(lo[a]); h->dp.thi[a] = hi[a] + margin + 1e-5f * std::fabs(hi[a]); }
   h->dp.tri = h->tri_dev; h->dp.n_tri = (int)count;
+  update_obstacle_box(h);
   return PBF_OK;
 }
 

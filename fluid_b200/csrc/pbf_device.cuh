@@ -24,6 +24,7 @@ struct DevParams {
   float bmin[3], bmax[3];     // collision box
   float clo[3], chi[3];       // hard clamp bounds: bmin + eps_d, bmax - eps_d
   float slo[3], shi[3];       // "clear of every plane" bounds: box and virtual planes shrunk by a margin >> rounding
+  float olo[3], ohi[3];       // bounding box of all obstacles (spheres, triangles) plus a margin; empty when there are none
   float yl, zf;               // virtual planes
   // uniform grid (cell edge slightly larger than h => 27-cell search is conservative)
   // Along z (the fastest axis of the linear cell id) every cell is split into `zsub` thin cells of edge cell/zsub:
@@ -166,14 +167,18 @@ __device__ __forceinline__ bool ex_mesh_hit(const DevParams& P, float3 o, float3
 // launched when the scene has none, so box-only scenes pay nothing for them).
 template <bool SPH>
 __device__ __forceinline__ float3 ex_collide(const DevParams& P, float3 p, float3 delta, bool respond) {
-  if (!SPH) {
+  {
     // Fast path for the bulk of the fluid: start and end point both clear of every wall and virtual plane by a
-    // margin far above any rounding, so the general path below would find no hit and return exactly p + delta
-    // (its hard clamp is then the identity).  |delta| <= eps_d (returns p unchanged) goes the general way.
+    // margin far above any rounding (and, with obstacles, the move's bounding box clear of the obstacles' box), so
+    // the general path below would find no hit and return exactly p + delta (its hard clamp is then the
+    // identity).  |delta| <= eps_d (returns p unchanged) goes the general way.
     const float3 q = make_float3(__fadd_rn(p.x, delta.x), __fadd_rn(p.y, delta.y), __fadd_rn(p.z, delta.z));
-    const bool clear = p.x > P.slo[0] && p.x < P.shi[0] && q.x > P.slo[0] && q.x < P.shi[0] &&
-                       p.y > P.slo[1] && p.y < P.shi[1] && q.y > P.slo[1] && q.y < P.shi[1] &&
-                       p.z > P.slo[2] && p.z < P.shi[2] && q.z > P.slo[2] && q.z < P.shi[2];
+    bool clear = p.x > P.slo[0] && p.x < P.shi[0] && q.x > P.slo[0] && q.x < P.shi[0] &&
+                 p.y > P.slo[1] && p.y < P.shi[1] && q.y > P.slo[1] && q.y < P.shi[1] &&
+                 p.z > P.slo[2] && p.z < P.shi[2] && q.z > P.slo[2] && q.z < P.shi[2];
+    if (SPH)
+      clear = clear && (fmaxf(p.x, q.x) < P.olo[0] || fminf(p.x, q.x) > P.ohi[0] || fmaxf(p.y, q.y) < P.olo[1] || fminf(p.y, q.y) > P.ohi[1] ||
+                        fmaxf(p.z, q.z) < P.olo[2] || fminf(p.z, q.z) > P.ohi[2]);
     if (clear && ex_norm2(delta.x, delta.y, delta.z) > 1e-20f) return q;
   }
   const float total_l = __fsqrt_rn(ex_norm2(delta.x, delta.y, delta.z));

@@ -478,7 +478,7 @@ __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, u
 }
 
 template <int NCORR, bool SPH>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, SPH ? 6 : 1)   // obstacle instantiation: capped at 40 registers = 6 CTAs per SM like the box-only one (38)
 k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
         const uint32_t* __restrict__ nbr_cnt) {

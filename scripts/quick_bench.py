@@ -19,7 +19,19 @@ def main():
     box_max = (max(30.0, 0.3 * nx), max(15.0, 0.15 * ny), 0.1 * nz + 0.1)
     p = api.default_params(rest_density=700.0, iterations=iters, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
     s = api.Solver(p)
+    if os.environ.get("QB_OBSTACLES"):      # two spheres and a cuboid standing in the block (particles inside them are left out)
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import helpers as H
+        sph = np.array([[0.05 * nx, 0.0, 0.05 * nz, 0.04 * nz], [0.08 * nx, 0.03 * ny, 0.03 * nz, 0.02 * nz]])
+        lo, hi = (0.02 * nx, 0.0, 0.06 * nz), (0.03 * nx, 0.05 * ny, 0.09 * nz)
+        s.set_obstacle_spheres(sph); s.set_obstacle_triangles(H.box_mesh(lo, hi))
     pos, vel = block(nx, ny, nz)
+    if os.environ.get("QB_OBSTACLES"):
+        keep = np.ones(len(pos), dtype=bool)
+        for c in sph:
+            keep &= np.linalg.norm(pos - c[:3], axis=1) > c[3] + 0.02
+        keep &= ~np.all((pos > np.array(lo) - 0.02) & (pos < np.array(hi) + 0.02), axis=1)
+        pos, vel = pos[keep], vel[keep]
     n = pos.shape[0]
     t0 = time.time(); s.upload(pos, vel); t_up = time.time() - t0
     s.step(2)   # warm-up
