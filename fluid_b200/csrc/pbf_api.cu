@@ -72,7 +72,15 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.shi[2] = std::min(d.shi[2], d.zf - 1e-4f * (1.0f + std::fabs(d.zf)));
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
-  d.n_sph = 0; d.n_sm = 148; d.n_tri = 0; d.tri = nullptr;
+  d.n_sph = 0; d.n_sm = 148; d.n_tri = 0; d.tri = nullptr; d.bvh = nullptr; d.tri_id = nullptr;
+  {   // fp32 contact rules of the obstacle triangles: same expressions (in double) as Oracle<float>'s constructor
+    double m = 0;
+    for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs((double)p.box_min[a]), std::fabs((double)p.box_max[a])));
+    const double ulp = m * 1.1920928955078125e-07;
+    d.skin = (float)std::max(1e-5 * (double)p.h, 16.0 * ulp);
+    d.tol_n = (float)(std::max(1e-4 * (double)p.h, 64.0 * ulp) + std::max(1e-5 * (double)p.h, 16.0 * ulp));
+    d.tol_ray = (float)std::max(0.05 * (double)p.h, 16.0 * std::max(1e-4 * (double)p.h, 64.0 * ulp));
+  }
   for (int a = 0; a < 3; a++) { d.tlo[a] = 0.f; d.thi[a] = 0.f; d.olo[a] = 1e30f; d.ohi[a] = -1e30f; }
   for (int k = 0; k < PBF_MAX_SPHERES; k++) { d.sph[k] = make_float4(0.f, 0.f, 0.f, 0.f); d.sph_r2[k] = 0.f; }
   return PBF_OK;
@@ -260,7 +268,7 @@ void pbf_destroy(pbf_handle* h) {
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   delete static_cast<HandleExtra*>(h->host_extra);
-  cudaFree(h->tri_dev);
+  cudaFree(h->tri_dev); cudaFree(h->bvh_dev); cudaFree(h->tri_id_dev);
   delete h;
 }
 
@@ -417,7 +425,7 @@ static void update_obstacle_box(pbf_handle* h) {
     for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[a] - d.sph[k].w); hi[a] = std::max(hi[a], c[a] + d.sph[k].w); }
   }
   if (d.n_tri > 0) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], d.tlo[a]); hi[a] = std::max(hi[a], d.thi[a]); }
-  const float margin = 1e-2f * d.h;
+  const float margin = 1e-2f * d.h + d.tol_ray + 2.f * d.skin;
   for (int a = 0; a < 3; a++) { d.olo[a] = lo[a] - margin - 1e-5f * std::fabs(lo[a]); d.ohi[a] = hi[a] + margin + 1e-5f * std::fabs(hi[a]); }
 }
 
@@ -439,8 +447,47 @@ int pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* s) {
   return PBF_OK;
 }
 
-// Obstacle triangles (small meshes; every particle whose move touches the mesh's bounding box tests all of them).
-// Edges, orientation and |e1 x e2| are precomputed in fp32 with the same single roundings as Oracle<float>::set_triangles.
+// Bounding-volume hierarchy over the obstacle triangles, built on the host once per pbf_set_obstacle_triangles and
+// walked on the device by ex_mesh_hit (the reference keeps its primitives in BVHAccel, bvh.cpp:48-140; this is a
+// new hierarchy, not that one: median split of the centroids along the widest axis, leaves of <= 4 triangles,
+// children of an inner node adjacent).  Node = 2 float4: (lo.xyz, a), (hi.xyz, b) with the integers stored as bits.
+namespace {
+struct BvhBuild {
+  const std::vector<float>& tb;            // per triangle: lo[3], hi[3], centroid[3]
+  std::vector<uint32_t> order;             // leaf order -> original triangle index
+  std::vector<float> nodes;                // 8 floats per node
+  int max_depth = 0;
+  explicit BvhBuild(const std::vector<float>& boxes) : tb(boxes) {}
+  static void put_int(float* dst, int v) { std::memcpy(dst, &v, sizeof(int)); }
+  void build(uint32_t node, uint32_t first, uint32_t count, int depth) {
+    max_depth = std::max(max_depth, depth);
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (uint32_t k = first; k < first + count; k++) {
+      const float* b = &tb[9 * order[k]];
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[3 + a]);
+        clo[a] = std::min(clo[a], b[6 + a]); chi[a] = std::max(chi[a], b[6 + a]);
+      }
+    }
+    for (int a = 0; a < 3; a++) { nodes[8 * node + a] = lo[a]; nodes[8 * node + 4 + a] = hi[a]; }
+    if (count <= 4) { put_int(&nodes[8 * node + 3], (int)first); put_int(&nodes[8 * node + 7], (int)count); return; }
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    const uint32_t half = count / 2;
+    std::nth_element(order.begin() + first, order.begin() + first + half, order.begin() + first + count,
+                     [&](uint32_t x, uint32_t y) { const float cx = tb[9 * x + 6 + axis], cy = tb[9 * y + 6 + axis]; return cx < cy || (cx == cy && x < y); });
+    const uint32_t left = (uint32_t)(nodes.size() / 8);
+    nodes.resize(nodes.size() + 16);
+    put_int(&nodes[8 * node + 3], (int)left); put_int(&nodes[8 * node + 7], 0);
+    build(left, first, half, depth + 1);
+    build(left + 1, first + half, count - half, depth + 1);
+  }
+};
+}  // namespace
+
+// Obstacle triangles.  Edges, orientation and |e1 x e2| are precomputed in fp32 with the same single roundings as
+// Oracle<float>::set_triangles; the records are stored in the leaf order of the hierarchy above.
 int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   if (!h || (count && !q)) return fail(h, PBF_ERR_INVALID, "pbf_set_obstacle_triangles: null argument");
   if (count > PBF_MAX_TRIANGLES) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_triangles: more than PBF_MAX_TRIANGLES triangles");
@@ -449,10 +496,12 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   CK(h, cudaStreamSynchronize(h->stream));            // kernels in flight still read the old list
   h->graph_invalidate();
   if (h->tri_dev) { cudaFree(h->tri_dev); h->tri_dev = nullptr; }
-  h->dp.n_tri = 0; h->dp.tri = nullptr;
+  if (h->bvh_dev) { cudaFree(h->bvh_dev); h->bvh_dev = nullptr; }
+  if (h->tri_id_dev) { cudaFree(h->tri_id_dev); h->tri_id_dev = nullptr; }
+  h->dp.n_tri = 0; h->dp.tri = nullptr; h->dp.bvh = nullptr; h->dp.tri_id = nullptr;
   update_obstacle_box(h);
   if (count == 0) return PBF_OK;
-  std::vector<float> t(20 * count);
+  std::vector<float> t(20 * count), tb(9 * count);
   float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
   for (size_t k = 0; k < count; k++) {
     volatile float v[18];
@@ -473,13 +522,38 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
     for (int a = 0; a < 9; a++) o[9 + a] = v[9 + a];
     o[18] = dsum < 0.f ? -1.f : 1.f;                    // orientation of e1 x e2 against the vertex normals
     o[19] = std::sqrt((float)qs);                       // |e1 x e2|
-    for (int p3 = 0; p3 < 3; p3++) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], (float)v[3 * p3 + a]); hi[a] = std::max(hi[a], (float)v[3 * p3 + a]); }
+    float* b = &tb[9 * k];
+    for (int a = 0; a < 3; a++) {
+      b[a] = std::min((float)v[a], std::min((float)v[3 + a], (float)v[6 + a]));
+      b[3 + a] = std::max((float)v[a], std::max((float)v[3 + a], (float)v[6 + a]));
+      b[6 + a] = 0.5f * (b[a] + b[3 + a]);
+      lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[3 + a]);
+    }
   }
-  CK(h, cudaMalloc((void**)&h->tri_dev, t.size() * sizeof(float)));
-  CK(h, cudaMemcpy(h->tri_dev, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-  const float margin = 1e-2f * h->dp.h;               // >> the contact tolerance (1e-4 h) and the inflated edges
+  BvhBuild B(tb);
+  B.order.resize(count);
+  for (size_t k = 0; k < count; k++) B.order[k] = (uint32_t)k;
+  B.nodes.reserve(8 * (count + 1));
+  B.nodes.resize(8);
+  B.build(0, 0, (uint32_t)count, 1);
+  if (B.max_depth > PBF_BVH_MAX_DEPTH) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_triangles: hierarchy deeper than the traversal stack");
+  const float margin = 1e-2f * h->dp.h + h->dp.tol_ray + 2.f * h->dp.skin;   // every accepted hit lies within tol_ray of the segment; plus the inflated edges and the rounding of a segment end
+  for (size_t nd = 0; nd < B.nodes.size() / 8; nd++)
+    for (int a = 0; a < 3; a++) {
+      float& l = B.nodes[8 * nd + a]; float& u = B.nodes[8 * nd + 4 + a];
+      l = l - margin - 1e-5f * std::fabs(l); u = u + margin + 1e-5f * std::fabs(u);
+    }
+  std::vector<float> ts(20 * count);
+  for (size_t k = 0; k < count; k++) std::memcpy(&ts[20 * k], &t[20 * (size_t)B.order[k]], 20 * sizeof(float));
+  CK(h, cudaMalloc((void**)&h->tri_dev, ts.size() * sizeof(float)));
+  CK(h, cudaMemcpy(h->tri_dev, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(h, cudaMalloc((void**)&h->bvh_dev, B.nodes.size() * sizeof(float)));
+  CK(h, cudaMemcpy(h->bvh_dev, B.nodes.data(), B.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(h, cudaMalloc((void**)&h->tri_id_dev, count * sizeof(uint32_t)));
+  CK(h, cudaMemcpy(h->tri_id_dev, B.order.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
   for (int a = 0; a < 3; a++) { h->dp.tlo[a] = lo[a] - margin - 1e-5f * std::fabs(lo[a]); h->dp.thi[a] = hi[a] + margin + 1e-5f * std::fabs(hi[a]); }
-  h->dp.tri = h->tri_dev; h->dp.n_tri = (int)count;
+  h->dp.tri = h->tri_dev; h->dp.bvh = h->bvh_dev; h->dp.tri_id = h->tri_id_dev; h->dp.n_tri = (int)count;
+  h->bvh_nodes = B.nodes.size() / 8; h->bvh_depth = B.max_depth;
   update_obstacle_box(h);
   return PBF_OK;
 }

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define PBF_BVH_MAX_DEPTH 40     // traversal stack; the host build refuses deeper hierarchies
+
 namespace pbf {
 
 // Parameters in working precision; filled on the host (pbf_api.cu) in plain IEEE float arithmetic.
@@ -40,9 +42,13 @@ struct DevParams {
   // obstacle spheres (pbf_set_obstacle_spheres): centre xyz, radius in .w; r^2 = r*r rounded once
   int   n_sm;                 // SMs of the device (tile order of the gather kernels)
   // obstacle triangles (pbf_set_obstacle_triangles): 5 float4 each = p1, e1 = p2-p1, e2 = p3-p1, n1, n2, n3, sg, ngl
-  // (sg = +-1 orientation of e1 x e2 against the vertex normals, ngl = |e1 x e2|); tlo / thi = bounding box + margin
+  // (sg = +-1 orientation of e1 x e2 against the vertex normals, ngl = |e1 x e2|), stored in the leaf order of the
+  // bounding-volume hierarchy `bvh` (see ex_mesh_hit); tri_id = original index of each; tlo / thi = bounding box + margin
   const float4* tri;
+  const float4* bvh;
+  const uint32_t* tri_id;
   int   n_tri;
+  float skin, tol_n, tol_ray;  // fp32 contact rules of the triangles (Oracle<float>: SKIN, TOL_N, TOL_RAY)
   float tlo[3], thi[3];
   int   n_sph;
   float4 sph[8];
@@ -128,35 +134,80 @@ __device__ __forceinline__ float3 ex_cross(float3 u, float3 v) {
   return make_float3(__fsub_rn(__fmul_rn(u.y, v.z), __fmul_rn(u.z, v.y)), __fsub_rn(__fmul_rn(u.z, v.x), __fmul_rn(u.x, v.z)),
                      __fsub_rn(__fmul_rn(u.x, v.y), __fmul_rn(u.y, v.x)));
 }
-__device__ __forceinline__ bool ex_mesh_hit(const DevParams& P, float3 o, float3 d, float& max_t, int& which, float3& nrm, int slid) {
-  // bounding-box reject: a hit point (or a contact within TOL_T) lies inside the mesh's box, which the segment must touch
-  const float3 q = make_float3(o.x + max_t * d.x, o.y + max_t * d.y, o.z + max_t * d.z);
-  if (fmaxf(o.x, q.x) < P.tlo[0] || fminf(o.x, q.x) > P.thi[0] || fmaxf(o.y, q.y) < P.tlo[1] || fminf(o.y, q.y) > P.thi[1] ||
-      fmaxf(o.z, q.z) < P.tlo[2] || fminf(o.z, q.z) > P.thi[2]) return false;
+// One triangle of the leaf order against the current best hit.  Acceptance = the oracle's sequential scan in ascending
+// triangle index with "t <= max_t" (later index wins a tie), written order-independently: strictly nearer, or equally
+// near with a larger ORIGINAL index, so the BVH's visiting order cannot change the result.
+__device__ __forceinline__ bool ex_tri_test(const DevParams& P, const float4* __restrict__ T, int id, float3 o, float3 d, float& max_t,
+                                            int& best, float3& nrm, int slid) {
   const float BT = 1e-6f, ONE_BT = __fadd_rn(1.f, 1e-6f), TOL_T = __fmul_rn(1e-4f, P.h), TAN = 1e-5f;
-  bool hit = false;
-  for (int k = 0; k < P.n_tri; k++) {
-    const float4* T = P.tri + 5 * k;
-    const float4 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2);
-    const float3 p1 = make_float3(a0.x, a0.y, a0.z), e1 = make_float3(a0.w, a1.x, a1.y), e2 = make_float3(a1.z, a1.w, a2.x);
-    const float3 s = make_float3(__fsub_rn(o.x, p1.x), __fsub_rn(o.y, p1.y), __fsub_rn(o.z, p1.z));
-    const float3 s1 = ex_cross(d, e2), s2 = ex_cross(s, e1);
-    const float dd = ex_dot(s1, e1);
-    const float4 a3 = __ldg(T + 3), a4 = __ldg(T + 4);
-    const float sg = a4.z, ngl = a4.w;
-    if (!(__fmul_rn(sg, dd) > (k == slid ? __fmul_rn(TAN, ngl) : 0.f))) continue;
-    float t = __fdiv_rn(ex_dot(s2, e2), dd);
-    if (t < 0.f) { if (t >= -TOL_T) t = 0.f; else continue; }
-    if (t > max_t) continue;
-    const float u = __fdiv_rn(ex_dot(s1, s), dd), v = __fdiv_rn(ex_dot(s2, d), dd), w = __fsub_rn(__fsub_rn(1.f, u), v);
-    if ((u < -BT) || (u > ONE_BT) || (v < -BT) || (v > ONE_BT) || (w < -BT) || (w > ONE_BT)) continue;
-    const float3 n1 = make_float3(a2.y, a2.z, a2.w), n2 = make_float3(a3.x, a3.y, a3.z), n3 = make_float3(a3.w, a4.x, a4.y);
-    max_t = t; which = k; hit = true;
-    nrm = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(w, n1.x), __fmul_rn(u, n2.x)), __fmul_rn(v, n3.x)),
-                      __fadd_rn(__fadd_rn(__fmul_rn(w, n1.y), __fmul_rn(u, n2.y)), __fmul_rn(v, n3.y)),
-                      __fadd_rn(__fadd_rn(__fmul_rn(w, n1.z), __fmul_rn(u, n2.z)), __fmul_rn(v, n3.z)));
+  const float4 a0 = __ldg(T), a1 = __ldg(T + 1), a2 = __ldg(T + 2);
+  const float3 p1 = make_float3(a0.x, a0.y, a0.z), e1 = make_float3(a0.w, a1.x, a1.y), e2 = make_float3(a1.z, a1.w, a2.x);
+  const float3 s = make_float3(__fsub_rn(o.x, p1.x), __fsub_rn(o.y, p1.y), __fsub_rn(o.z, p1.z));
+  const float3 s1 = ex_cross(d, e2), s2 = ex_cross(s, e1);
+  const float dd = ex_dot(s1, e1);
+  const float4 a3 = __ldg(T + 3), a4 = __ldg(T + 4);
+  const float sg = a4.z, ngl = a4.w;
+  if (!(__fmul_rn(sg, dd) > (id == slid ? __fmul_rn(TAN, ngl) : 0.f))) return false;
+  float t = __fdiv_rn(ex_dot(s2, e2), dd);
+  const float add = fabsf(dd);
+  const float shift = __fdiv_rn(__fmul_rn(P.skin, ngl), add);     // rest a skin in front of the plane (fp32 contact rule, see the oracle)
+  t = __fsub_rn(t, shift < P.tol_ray ? shift : P.tol_ray);
+  if (t < 0.f) {
+    if (t >= -TOL_T) t = 0.f;
+    else if (t >= -P.tol_ray && __fmul_rn(-t, add) <= __fmul_rn(P.tol_n, ngl)) t = 0.f;   // at most tol_n behind the skin
+    else return false;
   }
-  return hit;
+  if (t > max_t || (t == max_t && best >= 0 && id < best)) return false;
+  const float u = __fdiv_rn(ex_dot(s1, s), dd), v = __fdiv_rn(ex_dot(s2, d), dd), w = __fsub_rn(__fsub_rn(1.f, u), v);
+  if ((u < -BT) || (u > ONE_BT) || (v < -BT) || (v > ONE_BT) || (w < -BT) || (w > ONE_BT)) return false;
+  const float3 n1 = make_float3(a2.y, a2.z, a2.w), n2 = make_float3(a3.x, a3.y, a3.z), n3 = make_float3(a3.w, a4.x, a4.y);
+  max_t = t; best = id;
+  nrm = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(w, n1.x), __fmul_rn(u, n2.x)), __fmul_rn(v, n3.x)),
+                    __fadd_rn(__fadd_rn(__fmul_rn(w, n1.y), __fmul_rn(u, n2.y)), __fmul_rn(v, n3.y)),
+                    __fadd_rn(__fadd_rn(__fmul_rn(w, n1.z), __fmul_rn(u, n2.z)), __fmul_rn(v, n3.z)));
+  return true;
+}
+
+// Nearest one-sided hit of the segment [o, o + max_t d] with the obstacle mesh.  The triangles sit in the leaf order of a
+// bounding-volume hierarchy built on the host (pbf_set_obstacle_triangles: 2 float4 per node = (lo, a), (hi, b); a leaf
+// holds triangles [a, a+b) of the leaf order, an inner node (b = 0) has its children at a and a+1).  A subtree is
+// skipped when the segment's bounding box misses the node's box; node boxes carry a margin above tol_ray (every hit
+// the scan accepts lies within tol_ray of the segment), the inflated edges and any rounding of the segment end, so no
+// triangle the scan would accept is skipped
+// and the result equals the oracle's scan over ALL triangles bit for bit (the reference keeps the same primitives in
+// BVHAccel, bvh.cpp:48-192).  `which` = ORIGINAL triangle index.
+__device__ __forceinline__ bool ex_mesh_hit(const DevParams& P, float3 o, float3 d, float& max_t, int& which, float3& nrm, int slid) {
+  float3 q = make_float3(o.x + max_t * d.x, o.y + max_t * d.y, o.z + max_t * d.z);
+  float3 lo = make_float3(fminf(o.x, q.x), fminf(o.y, q.y), fminf(o.z, q.z));
+  float3 hi = make_float3(fmaxf(o.x, q.x), fmaxf(o.y, q.y), fmaxf(o.z, q.z));
+  if (hi.x < P.tlo[0] || lo.x > P.thi[0] || hi.y < P.tlo[1] || lo.y > P.thi[1] || hi.z < P.tlo[2] || lo.z > P.thi[2]) return false;
+  int stack[PBF_BVH_MAX_DEPTH];
+  int sp = 0, node = 0, best = -1;
+  for (;;) {
+    const float4 n0 = __ldg(P.bvh + 2 * node), n1 = __ldg(P.bvh + 2 * node + 1);
+    bool descend = false;
+    if (!(hi.x < n0.x || lo.x > n1.x || hi.y < n0.y || lo.y > n1.y || hi.z < n0.z || lo.z > n1.z)) {
+      const int a = __float_as_int(n0.w), b = __float_as_int(n1.w);
+      if (b > 0) {
+        bool any = false;
+        for (int k = a; k < a + b; k++)
+          if (ex_tri_test(P, P.tri + 5 * k, (int)__ldg(P.tri_id + k), o, d, max_t, best, nrm, slid)) any = true;
+        if (any) {       // the segment got shorter
+          q = make_float3(o.x + max_t * d.x, o.y + max_t * d.y, o.z + max_t * d.z);
+          lo = make_float3(fminf(o.x, q.x), fminf(o.y, q.y), fminf(o.z, q.z));
+          hi = make_float3(fmaxf(o.x, q.x), fmaxf(o.y, q.y), fmaxf(o.z, q.z));
+        }
+      } else {
+        stack[sp++] = a + 1; node = a; descend = true;
+      }
+    }
+    if (!descend) {
+      if (sp == 0) break;
+      node = stack[--sp];
+    }
+  }
+  if (best >= 0) which = best;
+  return best >= 0;
 }
 
 // Swept move of p by delta against the box: clamp() (respond=false, particles.cpp:51-84) and

@@ -62,7 +62,10 @@ struct Solver {
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
   void* host_extra = nullptr;        // pbf_api.cu's HandleExtra (pinned staging, registered host ranges)
-  float4* tri_dev = nullptr;         // obstacle triangles (5 float4 each), referenced by dp.tri
+  float4* tri_dev = nullptr;         // obstacle triangles (5 float4 each, leaf order), referenced by dp.tri
+  float4* bvh_dev = nullptr;         // their bounding-volume hierarchy (2 float4 per node), dp.bvh
+  uint32_t* tri_id_dev = nullptr;    // leaf order -> original triangle index, dp.tri_id
+  size_t bvh_nodes = 0; int bvh_depth = 0;
   int capture_xpred = 0;
   bool have_neighbors = false;
   long long rebinned_at = -1;

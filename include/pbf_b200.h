@@ -87,11 +87,12 @@ int  pbf_device_count(void);                    /* 0 when no CUDA device is visi
 int  pbf_set_obstacle_spheres(pbf_handle* h, size_t count, const double* cx_cy_cz_r);
 /* Obstacle triangles, 18 doubles each (p1, p2, p3, then the vertex normals n1, n2, n3): the triangle primitives
  * (StaticScene::Triangle / MarchingTriangle, triangle.cpp:21-80, marching_triangle.cpp:21-73) of the BVH the
- * reference collides against, for small meshes: every particle whose move touches the mesh's bounding box tests all
- * triangles (no device BVH).  Rules: a triangle blocks only motion against its oriented normal
- * (orientation = the side the vertex normals point to), nearest hit of walls, spheres and triangles, one slide
- * along the plane given by the interpolated vertex normals in the predict pass. */
-#define PBF_MAX_TRIANGLES 4096
+ * reference collides against (bvh.cpp:48-192).  A bounding-volume hierarchy over them is built on the host here and
+ * walked on the device; its result is, bit for bit, that of testing every triangle in index order.  Rules (DESIGN.md
+ * §2): a triangle blocks only motion against its oriented normal (orientation = the side the vertex normals point
+ * to), nearest hit of walls, spheres and triangles (equally near: the larger index), one slide along the plane
+ * given by the interpolated vertex normals in the predict pass.  Replaces the previous set; count 0 removes it. */
+#define PBF_MAX_TRIANGLES (1u << 22)
 int  pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* p1_p2_p3_n1_n2_n3);
 
 /* ---- state in / out (host buffers, original order, doubles) ----------------------------- */

@@ -85,6 +85,7 @@ struct Oracle {
   R H, H2, H6, H9, DT, RHO0, EPS_RELAX, KCORR, VISC, VORT_EPS, GRAV, EPS_D, TSCALE;
   int NCORR, ITERS;
   V bmin, bmax; R YL, ZF;
+  R SKIN, TOL_N, TOL_RAY;          // fp32-only contact rules of the obstacle triangles (0 in fp64)
   std::vector<Tri<R>> tris;       // the five walls (10 triangles)
   std::vector<Sph<R>> spheres;
   std::vector<Tri<R>> mesh;       // obstacle triangles (any MarchingTriangle / Triangle primitives of the scene's BVH)
@@ -105,6 +106,16 @@ struct Oracle {
     bmin = V(R(p.box_min[0]), R(p.box_min[1]), R(p.box_min[2]));
     bmax = V(R(p.box_max[0]), R(p.box_max[1]), R(p.box_max[2]));
     YL = R(p.y_light); ZF = R(p.z_front);
+    // fp32 contact rules of the obstacle triangles scale with the resolution of a coordinate (see mesh_hit_onesided)
+    SKIN = TOL_N = R(0); TOL_RAY = R(0);
+    if (sizeof(R) == 4) {
+      double m = 0;
+      for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs((double)p.box_min[a]), std::fabs((double)p.box_max[a])));
+      const double ulp = m * 1.1920928955078125e-07;
+      SKIN = R(std::max(1e-5 * (double)p.h, 16.0 * ulp));
+      TOL_N = R(std::max(1e-4 * (double)p.h, 64.0 * ulp) + std::max(1e-5 * (double)p.h, 16.0 * ulp));
+      TOL_RAY = R(std::max(0.05 * (double)p.h, 16.0 * std::max(1e-4 * (double)p.h, 64.0 * ulp)));
+    }
     // particles.cpp:151  tensile_instability_scale = 1 / poly6(0,0,0.1*H)
     TSCALE = R(1) / poly6(V(R(0), R(0), R(p.dq_ratio) * H));
     build_walls();
@@ -362,6 +373,14 @@ struct Oracle {
   // the surface and the triangle must be re-tested; it blocks the slide only when the direction dips below the
   // tangent plane by more than TAN (rounding of an exactly tangent direction must not freeze the particle).
   // In fp64 (BT = 0) this differs from the reference's two-sided test only for origins behind a triangle.
+  // fp32 only, so that nothing leaks where a coordinate resolves no better than ~1e-5 (|x| ~ 100): the hit distance is
+  // shortened so that a particle comes to rest SKIN = max(1e-5 h, 16 ulp) in front of the plane (measured along the
+  // normal) instead of +-1 ulp around it, and an origin up to TOL_N = max(1e-4 h, 64 ulp) + SKIN behind that skin
+  // surface (again along the normal, not along the ray: a grazing ray reaches far for a small depth) is still in
+  // contact.  Both reach at most TOL_RAY along the ray, so every accepted hit point lies within TOL_RAY of the
+  // segment [o, o + max_t d] (what a bounding-volume hierarchy over the triangles may rely on).
+  // (ulp = 2^-23 x the largest box coordinate.)  The barycentric test stays that of the UNSHIFTED plane: shifted
+  // copies of the triangles would leave gaps along convex edges.
   bool mesh_hit_onesided(const V& o, const V& d, R& max_t, int* which, V* nrm, int slid) const {
     const R BT = sizeof(R) == 4 ? R(1e-6) : R(0), TOL_T = R(1e-4) * H, TAN = R(1e-5);
     bool hit = false;
@@ -372,7 +391,15 @@ struct Oracle {
       R dd = dot(s1, e1);                         // = -d . (e1 x e2)
       if (!(T.sg * dd > (k == slid ? TAN * T.ngl : R(0)))) continue;   // moving away from / parallel to the front side
       R t = dot(s2, e2) / dd;
-      if (t < R(0)) { if (t >= -TOL_T) t = R(0); else continue; }
+      if (sizeof(R) == 4) {                       // stop a skin in front of the plane: SKIN along the normal = SKIN |n| / |dd| along the ray
+        const R shift = (SKIN * T.ngl) / std::fabs(dd);
+        t = t - (shift < TOL_RAY ? shift : TOL_RAY);
+      }
+      if (t < R(0)) {
+        if (t >= -TOL_T) t = R(0);
+        else if (sizeof(R) == 4 && t >= -TOL_RAY && (-t) * std::fabs(dd) <= TOL_N * T.ngl) t = R(0);   // at most TOL_N behind the skin
+        else continue;
+      }
       if (t > max_t) continue;
       R u = dot(s1, s) / dd, v = dot(s2, d) / dd, w = R(1) - u - v;
       if ((u < -BT) || (u > R(1) + BT) || (v < -BT) || (v > R(1) + BT) || (w < -BT) || (w > R(1) + BT)) continue;

@@ -25,7 +25,19 @@ def main():
         sph = np.array([[0.05 * nx, 0.0, 0.05 * nz, 0.04 * nz], [0.08 * nx, 0.03 * ny, 0.03 * nz, 0.02 * nz]])
         lo, hi = (0.02 * nx, 0.0, 0.06 * nz), (0.03 * nx, 0.05 * ny, 0.09 * nz)
         s.set_obstacle_spheres(sph); s.set_obstacle_triangles(H.box_mesh(lo, hi))
+    mesh_c = None
+    if os.environ.get("QB_MESH"):           # a tessellated sphere (2 * nlon * (nlat - 1) triangles, nlon = 2 nlat) standing in the block: device BVH
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import helpers as H
+        nlat = int(os.environ["QB_MESH"])
+        mesh_c = (0.05 * nx, 0.0, 0.05 * nz, 0.04 * nz)
+        t0 = time.time(); tris = H.uv_sphere_mesh(mesh_c[:3], mesh_c[3], nlat, 2 * nlat); t_gen = time.time() - t0
+        t0 = time.time(); s.set_obstacle_triangles(tris); t_set = time.time() - t0
+        print(f"mesh: {len(tris)} triangles, generated in {t_gen:.1f} s, pbf_set_obstacle_triangles (host BVH build + upload) {t_set:.3f} s", file=sys.stderr)
     pos, vel = block(nx, ny, nz)
+    if mesh_c is not None:
+        keep = np.linalg.norm(pos - np.array(mesh_c[:3]), axis=1) > mesh_c[3] + 0.02
+        pos, vel = pos[keep], vel[keep]
     if os.environ.get("QB_OBSTACLES"):
         keep = np.ones(len(pos), dtype=bool)
         for c in sph:
@@ -48,6 +60,8 @@ def main():
                particle_iter_per_s=n * iters * steps / (ms2 * 1e-3), avg_rho=(a, b), mean_nbrs=float(c.mean()), max_nbrs=int(c.max()),
                upload_s=t_up, download_s=t_down,
                kernels={k: dict(ms_per_step=v[0] / steps, launches_per_step=v[1] / steps) for k, v in prof.items() if v[1]})
+    if mesh_c is not None:
+        out["inside_mesh"] = int((np.linalg.norm(P - np.array(mesh_c[:3]), axis=1) < mesh_c[3] * 0.999).sum())
     print(json.dumps(out, indent=1))
 
 main()

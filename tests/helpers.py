@@ -300,3 +300,42 @@ def write_tris(path, tris):
     t = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
     with open(path, "wb") as f:
         f.write(np.int64(t.shape[0]).tobytes()); f.write(t.tobytes())
+
+
+def uv_sphere_mesh(center, r, nlat=48, nlon=96):
+    """Closed latitude/longitude sphere, counter-clockwise seen from outside, smooth (radial, unit) vertex normals:
+    2 * nlon * (nlat - 1) triangles.  A stand-in for the reference's large obstacle meshes (dae/sky/CBbunny.dae ...)."""
+    c = np.asarray(center, dtype=np.float64)
+    th = np.linspace(0.0, np.pi, nlat + 1)
+    ph = np.linspace(0.0, 2 * np.pi, nlon + 1)[:-1]
+
+    def nrm(i, j):
+        return np.array([np.sin(th[i]) * np.cos(ph[j % nlon]), np.cos(th[i]), np.sin(th[i]) * np.sin(ph[j % nlon])])
+    t = []
+    for i in range(nlat):
+        for j in range(nlon):
+            n00, n01, n10, n11 = nrm(i, j), nrm(i, j + 1), nrm(i + 1, j), nrm(i + 1, j + 1)
+            if i > 0:
+                t.append(np.concatenate([c + r * n00, c + r * n01, c + r * n10, n00, n01, n10]))
+            if i < nlat - 1:
+                t.append(np.concatenate([c + r * n01, c + r * n11, c + r * n10, n01, n11, n10]))
+    return np.array(t)
+
+
+def heightfield_mesh(x0, x1, z0, z1, nx, nz, base=0.12, amp=0.08, freq=9.0):
+    """Bumpy floor y = base + amp sin(freq x) cos(freq z) over [x0,x1] x [z0,z1], upward smooth vertex normals
+    (analytic gradient, unit length): 2 * nx * nz triangles."""
+    xs = np.linspace(x0, x1, nx + 1); zs = np.linspace(z0, z1, nz + 1)
+
+    def vert(i, k):
+        x, z = xs[i], zs[k]
+        y = base + amp * np.sin(freq * x) * np.cos(freq * z)
+        n = np.array([-amp * freq * np.cos(freq * x) * np.cos(freq * z), 1.0, amp * freq * np.sin(freq * x) * np.sin(freq * z)])
+        return np.array([x, y, z]), n / np.linalg.norm(n)
+    t = []
+    for i in range(nx):
+        for k in range(nz):
+            (a, na), (b, nb), (c, nc), (d, nd) = vert(i, k), vert(i, k + 1), vert(i + 1, k + 1), vert(i + 1, k)
+            t.append(np.concatenate([a, b, c, na, nb, nc]))
+            t.append(np.concatenate([a, c, d, na, nc, nd]))
+    return np.array(t)

@@ -14,6 +14,7 @@ import os
 import numpy as np
 import pytest
 
+import helpers as H
 from helpers import (ARRAY_LAMBDA, ARRAY_VORTICITY, ARRAY_XPRED, ARRAY_XSTAR, COLLIDE_BOX, COLLIDE_TRIANGLES, GOLDEN,
                      SEARCH_GRID, XSPH_JACOBI, Oracle, default_params as oracle_params, lattice_block, set_params)
 
@@ -517,12 +518,67 @@ def test_obstacle_triangles_whole_step_and_rollout():
     near_top = ((np.abs(P[:, 1] - 0.4) < 1e-3) & (P[:, 0] > -0.7) & (P[:, 0] < -0.2) & (P[:, 2] > -0.7) & (P[:, 2] < -0.2)).sum()
     assert near_top >= 1 or (P[:, 1] < 0.45).sum() > 0         # the fluid does reach the obstacles
     g.set_obstacle_triangles(np.zeros((0, 18))); g.step(1)      # removing them is allowed
-    with pytest.raises(api.PbfError) as e:
-        g.set_obstacle_triangles(np.tile(tris[0], (4097, 1)))
-    assert e.value.code == api.PBF_ERR_CAPACITY
     bad = tris.copy(); bad[3, 4] = np.inf
     with pytest.raises(api.PbfError):
         g.set_obstacle_triangles(bad)
+
+
+def _big_mesh_scene():
+    """~30k obstacle triangles (a smooth sphere under one block, a bumpy floor over the whole box; every 7th floor
+    triangle wound clockwise; 3000 triangles present twice with DIFFERENT vertex normals, so equally near hits exist and
+    the larger index must win; all in random order) and the upper layers of the jittered two-block scene above them."""
+    ref = np.load(os.path.join(GOLDEN, "ref_jitter_two_blocks.npz"))
+    pos, vel, rho0 = ref["pos"], ref["vel"], float(ref["rho0"])
+    keep = pos[:, 1] >= 0.75
+    pos, vel = pos[keep], vel[keep]
+    sph = H.uv_sphere_mesh((-0.5, 0.32, 0.5), 0.3)
+    hf = H.heightfield_mesh(-1.05, 1.05, -1.05, 1.05, 96, 96)            # covers the whole floor: nothing can get under it from the side
+    fl = hf[::7].copy()
+    fl[:, 3:6], fl[:, 6:9], fl[:, 12:15], fl[:, 15:18] = hf[::7, 6:9], hf[::7, 3:6], hf[::7, 15:18], hf[::7, 12:15]
+    hf[::7] = fl
+    tris = np.concatenate([sph, hf])
+    rng = np.random.default_rng(7)
+    dup = tris[rng.choice(len(tris), 3000, replace=False)].copy()
+    dup[:, 9:18] *= 0.8
+    tris = np.concatenate([tris, dup])
+    tris = tris[rng.permutation(len(tris))]
+    return pos, vel, rho0, tris
+
+
+def test_obstacle_mesh_hierarchy_equals_scan_over_all_triangles():
+    """Large obstacle meshes go through a bounding-volume hierarchy on the device; its nearest hit must be, bit for bit,
+    what the oracle's scan over ALL triangles in index order finds (including equally near hits on duplicated
+    triangles): predicted positions and neighbour sets exact from evolved states in contact with the meshes, whole
+    step inside the usual gates, nothing inside the sphere or under the floor after 45 free steps."""
+    pos, vel, rho0, tris = _big_mesh_scene()
+    assert len(tris) > 20000
+    g = _gpu(rho0); g.set_obstacle_triangles(tris); g.upload(pos, vel)
+    states = []
+    for steps in (12, 8, 10, 15):
+        g.step(steps)
+        P, V, _ = g.download()
+        states.append((P.copy(), V.copy()))
+    c = np.array([-0.5, 0.32, 0.5])
+    assert (np.linalg.norm(P - c, axis=1) < 0.3 * 0.995).sum() == 0
+    fy = 0.12 + 0.08 * np.sin(9.0 * P[:, 0]) * np.cos(9.0 * P[:, 2])
+    assert (P[:, 1] < fy - 2e-3).sum() == 0             # the tessellated floor is within 5e-4 of the analytic one
+    touched = 0
+    for k, (P, V) in enumerate(states):
+        gg = _gpu(rho0, iterations=0); gg.set_obstacle_triangles(tris); gg.capture(True); gg.upload(P, V); gg.step(1)
+        o = _oracle(rho0, 32, iterations=0); o.set_triangles(tris); o.upload(P, V); o.step(1)
+        xg = gg.array(ARRAY_XPRED); xo = o.array(ARRAY_XPRED)
+        assert np.array_equal(xg, xo), f"big mesh/state{k}: x* differs for {int(np.any(xg != xo, axis=1).sum())} particles (max {np.abs(xg - xo).max():.3e})"
+        assert np.array_equal(gg.neighbor_digest()[0], o.digest()[0]), f"big mesh/state{k}: neighbour digests differ"
+        g0 = _gpu(rho0, iterations=0); g0.capture(True); g0.upload(P, V); g0.step(1)
+        touched += int(np.any(g0.array(ARRAY_XPRED) != xg, axis=1).sum())
+    assert touched >= 50, touched
+    P, V = states[1]
+    gg = _gpu(rho0, iterations=4); gg.set_obstacle_triangles(tris); gg.upload(P, V); gg.step(1)
+    Pg, Vg, Rg = gg.download()
+    o = _oracle(rho0, 32, iterations=4); o.set_triangles(tris); o.upload(P, V); o.step(1)
+    Po, Vo, Ro = o.download()
+    assert np.array_equal(gg.neighbor_digest()[0], o.digest()[0])
+    _gate_whole_step("big mesh/state1 vs fp32 oracle", Pg, Rg, Po, Ro, rho0)
 
 
 def test_graph_replay_equals_plain_launches(monkeypatch):
