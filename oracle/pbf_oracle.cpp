@@ -111,6 +111,28 @@ void oracle_density_at(void* hv, size_t m, const double* q, double* out) {
   });
 }
 
+// Particles::getSurfacePrims restated (fp64 handle only): returns the number of triangles, writes at most cap (18 doubles each)
+size_t oracle_surface(void* hv, const double* lo, const double* hi, double iso, double step, double eps, size_t cap, double* out) {
+  Handle* h = (Handle*)hv;
+  if (!h->d) return 0;
+  std::vector<double> t = h->d->surface(lo, hi, iso, step, eps);
+  const size_t nt = t.size() / 18;
+  if (out) std::memcpy(out, t.data(), sizeof(double) * 18 * std::min(nt, cap));
+  return nt;
+}
+// marching.cpp polygonise for one sign pattern on the unit cell with corner values 0 (inside, bit set) / 1 and iso 0.5:
+// every vertex is an edge midpoint.  Returns the number of triangles (<= 5), 9 doubles each.
+int oracle_polygonise_case(int cube, double* out) {
+  typedef Oracle<double>::V V;
+  const V p[8] = {V(0, 0, 0), V(0, 1, 0), V(1, 1, 0), V(1, 0, 0), V(0, 0, 1), V(0, 1, 1), V(1, 1, 1), V(1, 0, 1)};
+  double val[8];
+  for (int i = 0; i < 8; i++) val[i] = ((cube >> i) & 1) ? 0.0 : 1.0;
+  std::vector<double> t;
+  Oracle<double>::polygonise(p, val, 0.5, t);
+  std::memcpy(out, t.data(), sizeof(double) * t.size());
+  return (int)(t.size() / 9);
+}
+
 size_t oracle_num_pairs(void* hv) {
   return visit((Handle*)hv, [&](auto& o) { return (size_t)o.col.size(); });
 }

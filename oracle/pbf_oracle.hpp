@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../include/pbf_b200.h"
+#include "../fluid_b200/csrc/pbf_mc_table.h"   // the marching-cubes table (data only; pinned by the reference fixture)
 
 namespace pbf_oracle {
 
@@ -503,6 +504,75 @@ struct Oracle {
     R d = R(0);
     for (size_t i = 0; i < n; i++) d += poly6(pos[i] - q);
     return d;
+  }
+
+  // ---- marching-cubes surface -------------------------------------------------
+  // marching.cpp:381-403 vertexInterp
+  static V vertex_interp(R iso, const V& p1, const V& p2, R v1, R v2) {
+    if (std::abs(iso - v1) < R(0.00001)) return p1;
+    if (std::abs(iso - v2) < R(0.00001)) return p2;
+    if (std::abs(v1 - v2) < R(0.00001)) return p1;
+    const R mu = (iso - v1) / (v2 - v1);
+    return V(p1.x + mu * (p2.x - p1.x), p1.y + mu * (p2.y - p1.y), p1.z + mu * (p2.z - p1.z));
+  }
+  // marching.cpp:17-380 polygonise: corner i is "inside" when val[i] < iso; appends 9 R per triangle
+  static void polygonise(const V p[8], const R val[8], R iso, std::vector<R>& out) {
+    static uint8_t table[256][16];
+    static bool ready = false;
+    if (!ready) {
+#pragma omp critical(pbf_mc_table)
+      { if (!ready) { pbf_mc::expand(table); ready = true; } }
+    }
+    int cube = 0;
+    for (int i = 0; i < 8; i++) if (val[i] < iso) cube |= 1 << i;
+    if (cube == 0 || cube == 255) return;            // edgeTable[cube] == 0
+    V vert[12];
+    for (int e = 0; e < 12; e++) {
+      const int a = pbf_mc::kEdgeCorner[e][0], b = pbf_mc::kEdgeCorner[e][1];
+      if (((cube >> a) & 1) != ((cube >> b) & 1)) vert[e] = vertex_interp(iso, p[a], p[b], val[a], val[b]);
+    }
+    for (int k = 0; table[cube][k] != 0xFF; k++) {
+      const V& q = vert[table[cube][k]];
+      out.push_back(q.x); out.push_back(q.y); out.push_back(q.z);
+    }
+  }
+  // particles.cpp:407-418 getVertexNormal: central differences of the density field, not divided by 2 eps
+  V vertex_normal(const V& q, R eps) const {
+    V nn(density_at(V(q.x - eps, q.y, q.z)) - density_at(V(q.x + eps, q.y, q.z)),
+         density_at(V(q.x, q.y - eps, q.z)) - density_at(V(q.x, q.y + eps, q.z)),
+         density_at(V(q.x, q.y, q.z - eps)) - density_at(V(q.x, q.y, q.z + eps)));
+    if (nn.norm() > R(0)) return nn.unit();
+    return nn;
+  }
+  // particles.cpp:352-391 getSurfacePrims over the lattice [lo, hi] (the reference hard-codes (-1,0,-1)..(1,1.5,1),
+  // particles.cpp:326-350): cells in ix / iy / iz order, the last cell of every axis clipped to hi (and of zero
+  // width when the step divides the extent); 18 R per triangle: p1 p2 p3 n1 n2 n3.
+  std::vector<R> surface(const R lo[3], const R hi[3], R iso, R step, R eps) const {
+    const int xs = (int)((hi[0] - lo[0]) / step), ys = (int)((hi[1] - lo[1]) / step), zs = (int)((hi[2] - lo[2]) / step);
+    const long long ncell = (long long)(xs + 1) * (ys + 1) * (zs + 1);
+    std::vector<std::vector<R>> per(ncell);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long c = 0; c < ncell; c++) {
+      const int iz = (int)(c % (zs + 1)), iy = (int)((c / (zs + 1)) % (ys + 1)), ix = (int)(c / ((long long)(zs + 1) * (ys + 1)));
+      const R x1 = lo[0] + ix * step, x2 = rmin(hi[0], x1 + step);
+      const R y1 = lo[1] + iy * step, y2 = rmin(hi[1], y1 + step);
+      const R z1 = lo[2] + iz * step, z2 = rmin(hi[2], z1 + step);
+      const V p[8] = {V(x1, y1, z1), V(x1, y2, z1), V(x2, y2, z1), V(x2, y1, z1), V(x1, y1, z2), V(x1, y2, z2), V(x2, y2, z2), V(x2, y1, z2)};
+      R val[8];
+      for (int i = 0; i < 8; i++) val[i] = density_at(p[i]);
+      std::vector<R> tri;
+      polygonise(p, val, iso, tri);
+      for (size_t t = 0; t + 9 <= tri.size(); t += 9) {
+        for (int k = 0; k < 9; k++) per[c].push_back(tri[t + k]);
+        for (int v = 0; v < 3; v++) {
+          const V nn = vertex_normal(V(tri[t + 3 * v], tri[t + 3 * v + 1], tri[t + 3 * v + 2]), eps);
+          per[c].push_back(nn.x); per[c].push_back(nn.y); per[c].push_back(nn.z);
+        }
+      }
+    }
+    std::vector<R> out;
+    for (long long c = 0; c < ncell; c++) out.insert(out.end(), per[c].begin(), per[c].end());
+    return out;
   }
 
   // particles.cpp:258-265: inclusive predicate on predicted positions, ascending index lists,

@@ -13,6 +13,10 @@
 //   --tris    adds MarchingTriangle obstacles (int64 count + 18 doubles each: p1 p2 p3 n1 n2 n3) to the BVH, after the spheres.
 //   --sphere  adds a StaticScene::Sphere obstacle to the BVH (the CBspheres scenes hold two r=0.3 spheres,
 //             dae/sky/CBspheres_lambertian.dae:291-305,575-594); repeatable.
+//   --surface s.bin : after the last step, Particles::getSurfacePrims(0.95 rho0, 0.3 * 0.5, nullptr) (what updateSurface
+//           calls, particles.cpp:393-402): int64 T, then 18 doubles per MarchingTriangle (p1 p2 p3 n1 n2 n3), in order.
+//   --mc-cases c.bin : polygonise() (marching.cpp:17) on the unit cell for all 256 sign patterns (corner value 0 where
+//           the bit is set, else 1; iso 0.5): per pattern int64 triangle count + 9 doubles per triangle.  No particles needed.
 //   q.bin : int64 M, M*3 doubles; d.bin : M doubles = Particles::estimateDensityAt(q) after the last
 //           step (particles.cpp:446-453, the field marching cubes samples).
 //   .bin input : int64 N, double rho0 (already rounded through float like stof, Q17),
@@ -35,8 +39,10 @@
 #include "CGL/CGL.h"
 #include "CGL/tinyxml2.h"
 #include "bvh.h"
-#include "particles.h"
+#include "particles.h"    // brings marching.h (no include guard there)
+#define private public      // this driver reads MarchingTriangle's vertices / normals to dump the surface (no source edit)
 #include "static_scene/marching_triangle.h"
+#undef private
 #include "static_scene/object.h"
 #include "static_scene/sphere.h"
 
@@ -92,7 +98,7 @@ static void add_quad(std::vector<Primitive*>& prims, Vector3D a, Vector3D b, Vec
 }
 
 int main(int argc, char** argv) {
-  const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr, *trisfile = nullptr;
+  const char *xml = nullptr, *bin = nullptr, *out = nullptr, *dq = nullptr, *dout = nullptr, *trisfile = nullptr, *surf = nullptr, *mccases = nullptr;
   int steps = 1; bool quiet = false;
   std::vector<double> spheres;
   for (int i = 1; i < argc; i++) {
@@ -106,7 +112,25 @@ int main(int argc, char** argv) {
     else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];
     else if (a == "--density-queries" && i + 1 < argc) dq = argv[++i];
     else if (a == "--density-out" && i + 1 < argc) dout = argv[++i];
+    else if (a == "--surface" && i + 1 < argc) surf = argv[++i];
+    else if (a == "--mc-cases" && i + 1 < argc) mccases = argv[++i];
     else { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
+  }
+  if (mccases) {
+    FILE* o = fopen(mccases, "wb");
+    if (!o) { fprintf(stderr, "cannot open %s\n", mccases); return 1; }
+    for (int c = 0; c < 256; c++) {
+      GridCell g;
+      g.p[0] = Vector3D(0, 0, 0); g.p[1] = Vector3D(0, 1, 0); g.p[2] = Vector3D(1, 1, 0); g.p[3] = Vector3D(1, 0, 0);
+      g.p[4] = Vector3D(0, 0, 1); g.p[5] = Vector3D(0, 1, 1); g.p[6] = Vector3D(1, 1, 1); g.p[7] = Vector3D(1, 0, 1);
+      for (int i = 0; i < 8; i++) g.val[i] = ((c >> i) & 1) ? 0.0 : 1.0;
+      std::vector<TriangleVertices*> t = polygonise(g, 0.5);
+      int64_t nt = (int64_t)t.size();
+      fwrite(&nt, 8, 1, o);
+      for (TriangleVertices* tv : t) for (int v = 0; v < 3; v++) { double q[3] = {tv->p[v].x, tv->p[v].y, tv->p[v].z}; fwrite(q, 8, 3, o); }
+    }
+    fclose(o);
+    return 0;
   }
   if ((!xml && !bin)) { fprintf(stderr, "need --xml or --bin\n"); return 2; }
 
@@ -195,6 +219,20 @@ int main(int argc, char** argv) {
     for (int64_t i = 0; i < m; i++) dens[i] = ps->estimateDensityAt(Vector3D(pts[3*i], pts[3*i+1], pts[3*i+2]));
     FILE* o = fopen(dout, "wb");
     fwrite(dens.data(), 8, m, o);
+    fclose(o);
+  }
+
+  if (surf) {
+    std::vector<Primitive*> sp = ps->getSurfacePrims(0.95 * ps->rest_density, 0.3 * 0.5, nullptr);
+    FILE* o = fopen(surf, "wb");
+    if (!o) { fprintf(stderr, "cannot open %s\n", surf); return 1; }
+    int64_t nt = (int64_t)sp.size();
+    fwrite(&nt, 8, 1, o);
+    for (Primitive* pr : sp) {
+      const MarchingTriangle* t = static_cast<const MarchingTriangle*>(pr);
+      const Vector3D* v[6] = {&t->p1, &t->p2, &t->p3, &t->n1, &t->n2, &t->n3};
+      for (int k = 0; k < 6; k++) { double q[3] = {v[k]->x, v[k]->y, v[k]->z}; fwrite(q, 8, 3, o); }
+    }
     fclose(o);
   }
 

@@ -12,6 +12,9 @@ Fixtures
                           prints, full state at steps 0/1/19 and the ordered neighbour CSR of step 0
   ref_sphere_<name>.npz   same with the CBspheres obstacle spheres in the reference's BVH (harness --sphere)
   ref_mesh_drop.npz       same with obstacle triangles (a cuboid and a wedge) in the reference's BVH (harness --tris)
+  ref_surface_<name>.npz  Particles::getSurfacePrims(0.95 rho0, 0.15) (= updateSurface, particles.cpp:393-402) of the
+                          unmodified reference after a few steps: the state and the triangle soup (18 doubles each)
+  mc_cases.npz            the reference's polygonise() (marching.cpp:17) on the unit cell for all 256 sign patterns
   ref_jitter_<name>.npz   same for jittered pgen-style inputs (lattice + U(-0.001,0.001),
                           default_rng(1234)) — the inputs used for fp32-vs-fp64 tolerance checks
 """
@@ -62,6 +65,33 @@ def reference_density_field(pos, vel, rho0, q):
             f.write(np.int64(q.shape[0]).tobytes()); f.write(np.ascontiguousarray(q, dtype=np.float64).tobytes())
         subprocess.run([ref_harness_path(), "--bin", scene, "--steps", "0", "--density-queries", qf, "--density-out", df, "--quiet"], check=True)
         return np.fromfile(df, dtype=np.float64)
+
+
+def reference_surface(pos, vel, rho0, steps):
+    """State after `steps` reference steps and the reference's own marching-cubes surface of it."""
+    with tempfile.TemporaryDirectory() as td:
+        scene = os.path.join(td, "scene.bin"); dump = os.path.join(td, "dump.bin"); sf = os.path.join(td, "surf.bin")
+        write_bin_scene(scene, pos, vel, rho0)
+        subprocess.run([ref_harness_path(), "--bin", scene, "--steps", str(steps), "--out", dump, "--surface", sf, "--quiet"], check=True)
+        d = read_dump(dump)
+        raw = np.fromfile(sf, dtype=np.uint8)
+        nt = int(raw[:8].view(np.int64)[0])
+        tris = raw[8:].view(np.float64).reshape(nt, 18).copy()
+        return d[-1]["state"].copy(), tris
+
+
+def reference_mc_cases():
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "cases.bin")
+        subprocess.run([ref_harness_path(), "--mc-cases", f], check=True)
+        raw = np.fromfile(f, dtype=np.uint8)
+    counts, verts, off = [], [], 0
+    for c in range(256):
+        nt = int(raw[off:off + 8].view(np.int64)[0]); off += 8
+        v = raw[off:off + 72 * nt].view(np.float64).reshape(nt, 9); off += 72 * nt
+        counts.append(nt); verts.append(v)
+    assert off == len(raw)
+    return np.array(counts), np.concatenate(verts)
 
 
 def pack(dump, log, keep):
@@ -158,5 +188,18 @@ def main():
         print("density field", name, q.shape[0], "points, max", d.max())
 
 
+def surface_fixtures():
+    for name, steps in (("p", 12), ("spheres_p", 30)):
+        sc = np.load(os.path.join(GOLDEN, f"scene_{name}.npz"))
+        st, tris = reference_surface(sc["pos"], sc["vel"], float(sc["rho0"]), steps)
+        np.savez_compressed(os.path.join(GOLDEN, f"ref_surface_{name}.npz"), state=st, tris=tris, rho0=float(sc["rho0"]), steps=steps)
+        print(f"ref_surface_{name}: {len(tris)} triangles after {steps} steps")
+    counts, verts = reference_mc_cases()
+    np.savez_compressed(os.path.join(GOLDEN, "mc_cases.npz"), counts=counts, verts=verts)
+    print(f"mc_cases: {counts.sum()} triangles over 256 patterns")
+
+
 if __name__ == "__main__":
+    if "--surface-only" in sys.argv:
+        surface_fixtures(); sys.exit(0)
     main()

@@ -72,6 +72,10 @@ def oracle_lib():
         lib.oracle_set_spheres.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.oracle_set_triangles.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.oracle_max_threads.restype = C.c_int
+        lib.oracle_surface.restype = C.c_size_t
+        lib.oracle_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_size_t, C.c_void_p]
+        lib.oracle_polygonise_case.restype = C.c_int
+        lib.oracle_polygonise_case.argtypes = [C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -147,6 +151,15 @@ class Oracle:
         self.lib.oracle_density_at(self.h, q.shape[0], _ptr(q), _ptr(out))
         return out
 
+    def surface(self, rho0, lo=(-1.0, 0.0, -1.0), hi=(1.0, 1.5, 1.0), iso_ratio=0.95, step=0.3 * 0.5, eps=0.001):
+        """Particles::getSurfacePrims as updateSurface calls it (particles.cpp:352-402): rows of 18 (p1 p2 p3 n1 n2 n3);
+        fp64 handles only."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64); hi = np.ascontiguousarray(hi, dtype=np.float64)
+        nt = self.lib.oracle_surface(self.h, _ptr(lo), _ptr(hi), iso_ratio * rho0, step, eps, 0, None)
+        out = np.empty((nt, 18))
+        self.lib.oracle_surface(self.h, _ptr(lo), _ptr(hi), iso_ratio * rho0, step, eps, nt, _ptr(out))
+        return out
+
     def neighbors(self):
         m = self.lib.oracle_num_pairs(self.h)
         row = np.empty(self.n + 1, dtype=np.uint32); col = np.empty(m, dtype=np.uint32)
@@ -162,6 +175,13 @@ class Oracle:
         a, b, ms = C.c_double(), C.c_double(), C.c_double()
         self.lib.oracle_stats(self.h, C.byref(a), C.byref(b), C.byref(ms))
         return a.value, b.value, ms.value
+
+
+def oracle_polygonise_case(cube):
+    """marching.cpp polygonise restated, unit cell, corner value 0 where the bit of `cube` is set else 1, iso 0.5."""
+    out = np.empty((5, 9))
+    nt = oracle_lib().oracle_polygonise_case(int(cube), _ptr(out))
+    return out[:nt].copy()
 
 
 # ---- reference harness -------------------------------------------------------------------------

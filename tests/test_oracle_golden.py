@@ -202,3 +202,34 @@ def test_density_field_matches_reference(name):
     o = Oracle(default_params(rest_density=float(ref["rho0"])), 64, COLLIDE_TRIANGLES, SEARCH_GRID)
     o.upload(ref["pos"], ref["vel"])
     assert np.array_equal(o.density_at(ref["q"]), ref["density"])
+
+
+# ---- marching-cubes surface ----------------------------------------------------
+
+def test_polygonise_table_matches_reference_for_all_256_patterns():
+    """The marching-cubes triangle table (fluid_b200/csrc/pbf_mc_table.h, used by the oracle and by the CUDA surfacer)
+    against the reference's own polygonise() (marching.cpp:17-380) on the unit cell for every sign pattern: same
+    triangles, same order, same vertex order."""
+    from helpers import oracle_polygonise_case
+    fx = np.load(os.path.join(GOLDEN, "mc_cases.npz"))
+    counts, verts = fx["counts"], fx["verts"]
+    assert counts.sum() == 820 and counts.max() == 5 and counts[0] == 0 and counts[255] == 0
+    off = 0
+    for c in range(256):
+        got = oracle_polygonise_case(c)
+        want = verts[off:off + counts[c]]; off += counts[c]
+        assert got.shape == want.shape and np.array_equal(got, want), c
+
+
+@pytest.mark.parametrize("name", ["p", "spheres_p"])
+def test_surface_matches_reference_fixture(name):
+    """Oracle restatement of Particles::getSurfacePrims (lattice, polygonise, vertexInterp, getVertexNormal;
+    particles.cpp:309-418, marching.cpp) == the unmodified reference's triangle soup on the reference's own state,
+    bit for bit: vertices and normals, in order."""
+    fx = np.load(os.path.join(GOLDEN, f"ref_surface_{name}.npz"))
+    st, want, rho0 = fx["state"], fx["tris"], float(fx["rho0"])
+    o = Oracle(default_params(rest_density=rho0), 64, COLLIDE_TRIANGLES, SEARCH_GRID)
+    o.upload(st[:, 0:3], st[:, 3:6])
+    got = o.surface(rho0)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got, want), f"{int(np.any(got != want, axis=1).sum())} triangles differ, max {np.abs(got - want).max():.3e}"
