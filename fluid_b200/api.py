@@ -68,6 +68,7 @@ def load_library():
         "pbf_estimate_densities": (i32, [vp]),
         "pbf_stats": (i32, [vp, vp, vp, vp]),
         "pbf_density_at": (i32, [vp, sz, vp, vp]),
+        "pbf_extract_surface": (i32, [vp, vp, vp, C.c_double, C.c_double, C.c_double, sz, vp, vp]),
         "pbf_upload_device": (i32, [vp, sz, vp, vp]),
         "pbf_download_device": (i32, [vp, vp, vp, vp]),
         "pbf_debug_neighbor_digest": (i32, [vp, vp, vp]),
@@ -191,6 +192,17 @@ class Solver:
         q = np.ascontiguousarray(query, dtype=np.float64)
         out = np.empty(q.shape[0])
         self._ck(self.lib.pbf_density_at(self.h, q.shape[0], _ptr(q), _ptr(out)))
+        return out
+
+    def extract_surface(self, rho0, lo=(-1.0, 0.0, -1.0), hi=(1.0, 1.5, 1.0), iso_ratio=0.95, step=0.3 * 0.5, eps=0.001):
+        """Particles::getSurfacePrims as updateSurface calls it (particles.cpp:352-402; the defaults are the reference's
+        hard-coded lattice and macros): [T,18] array, rows p1 p2 p3 n1 n2 n3, in the reference's triangle order."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64); hi = np.ascontiguousarray(hi, dtype=np.float64)
+        nt = C.c_size_t(0)
+        self._ck(self.lib.pbf_extract_surface(self.h, _ptr(lo), _ptr(hi), iso_ratio * rho0, step, eps, 0, None, C.byref(nt)))
+        out = np.empty((nt.value, 18))
+        if nt.value:
+            self._ck(self.lib.pbf_extract_surface(self.h, _ptr(lo), _ptr(hi), iso_ratio * rho0, step, eps, nt.value, _ptr(out), C.byref(nt)))
         return out
 
     def stats(self):

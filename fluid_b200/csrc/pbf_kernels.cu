@@ -1014,3 +1014,4 @@ void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count) {
 }  // namespace pbf
 
 #include "pbf_slab.inl"
+#include "pbf_surface.inl"

@@ -121,6 +121,17 @@ int  pbf_stats(pbf_handle* h, double* avg_rho_first_iter, double* avg_rho_final,
  * (particles.cpp:350-418).  Host fp64 AoS in, fp64 out; single GPU. */
 int  pbf_density_at(pbf_handle* h, size_t m, const double* query_xyz, double* density_out);
 
+/* Marching-cubes surface of the committed positions = Particles::getSurfacePrims (particles.cpp:352-391, called by
+ * updateSurface 393-402 with isolevel 0.95 rho0 and step 0.5 H) with marching.cpp's polygonise / vertexInterp and
+ * getVertexNormal (particles.cpp:407-418; grad_eps 0.001): lattice cells over [lo, hi] in ix / iy / iz order, the
+ * last cell of every axis clipped to hi.  Writes 18 doubles per triangle (p1 p2 p3 n1 n2 n3 = the arguments of the
+ * reference's MarchingTriangle constructor) for the first min(*n_triangles, cap_triangles) triangles in the
+ * reference's order; *n_triangles = the full count (call with cap 0 to size the buffer).  Everything runs on the
+ * device in fp64 on the fp32 state, every density term with the reference's operations; only the order of the
+ * sum differs, so the soup matches the reference's on the same state to ~1e-13.  Single GPU. */
+int  pbf_extract_surface(pbf_handle* h, const double lo[3], const double hi[3], double isolevel, double step, double grad_eps,
+                         size_t cap_triangles, double* tris_out, size_t* n_triangles);
+
 /* ---- device-resident I/O (bench "value" leg; fp32 xyz AoS device pointers, original order) */
 int  pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz);
 int  pbf_download_device(pbf_handle* h, float* d_pos_xyz, float* d_vel_xyz, float* d_density);
