@@ -111,6 +111,29 @@ void Particles::timeStep(double delta_t) {
 
 void Particles::timeStep() { timeStep(params_.dt); }             // DEFAULT_DELTA_T, particles.cpp:299-301
 
+std::vector<Particles::SurfaceTriangle> Particles::getSurfacePrims(double isolevel, double fStepSize) {
+  ensureUploaded();
+  const double lo[3] = {surface_min.x, surface_min.y, surface_min.z}, hi[3] = {surface_max.x, surface_max.y, surface_max.z};
+  const double grad_eps = 0.001;                                 // GRADIENT_EPS, particles.cpp:16
+  size_t nt = 0;
+  if (pbf_extract_surface(handle_, lo, hi, isolevel, fStepSize, grad_eps, 0, nullptr, &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  std::vector<double> buf(18 * nt);
+  if (nt && pbf_extract_surface(handle_, lo, hi, isolevel, fStepSize, grad_eps, nt, buf.data(), &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  std::vector<SurfaceTriangle> out(nt);
+  for (size_t t = 0; t < nt; t++) {
+    const double* q = &buf[18 * t];
+    out[t] = SurfaceTriangle{Vector3D(q[0], q[1], q[2]), Vector3D(q[3], q[4], q[5]), Vector3D(q[6], q[7], q[8]),
+                             Vector3D(q[9], q[10], q[11]), Vector3D(q[12], q[13], q[14]), Vector3D(q[15], q[16], q[17])};
+  }
+  return out;
+}
+
+void Particles::updateSurface() {                                // particles.cpp:393-402
+  if (surfaceUpToTimestep) return;
+  surface = getSurfacePrims(0.95 * rest_density, params_.h * 0.5);   // ISO_LEVEL_REST_DENSITY_RATIO, FSTEPSIZE_RATIO (particles.cpp:14,18)
+  surfaceUpToTimestep = true;
+}
+
 double Particles::estimateDensityAt(Vector3D pos) const {
   const double H = params_.h, H2 = H * H;
   double H9 = 1; for (int i = 0; i < 9; i++) H9 *= H;

@@ -48,6 +48,12 @@ struct Particles {
   double simulate_time;                // particles.h:109
   const double rest_density;           // particles.h:110
   bool surfaceUpToTimestep = false;    // particles.h:112
+  // particles.h:111 `std::vector<Primitive*> surface`: here the arguments of the reference's MarchingTriangle
+  // constructor (p1 p2 p3 n1 n2 n3), which is what PathTracer::build_accel turns into primitives (pathtracer.cpp:248-253)
+  struct SurfaceTriangle { Vector3D p1, p2, p3, n1, n2, n3; };
+  std::vector<SurfaceTriangle> surface;
+  // lattice of the surfacer: the reference hard-codes the Cornell box (particles.cpp:326-350)
+  Vector3D surface_min = Vector3D(-1, 0, -1), surface_max = Vector3D(1, 1.5, 1);
   bool quiet = false;                  // the reference prints two lines per step (Q16); keep, but allow silence
 
   explicit Particles(double rest_density = 1000.0, const PbfParams* params = nullptr, int device = 0);
@@ -65,6 +71,10 @@ struct Particles {
   void setObstacleSpheres(const std::vector<double>& cx_cy_cz_r);
   // ... and its triangle primitives (small meshes): 18 doubles each, p1 p2 p3 n1 n2 n3 (pbf_set_obstacle_triangles)
   void setObstacleTriangles(const std::vector<double>& p1_p2_p3_n1_n2_n3);
+  // Marching-cubes surface on the GPU (pbf_extract_surface): same triangles, same order as the reference's
+  // getSurfacePrims (particles.cpp:352-391) / updateSurface (393-402: isolevel 0.95 rho0, step 0.5 H)
+  std::vector<SurfaceTriangle> getSurfacePrims(double isolevel, double fStepSize);
+  void updateSurface();
   double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
   // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
   std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);

@@ -5,6 +5,8 @@
 //   pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--iterations I]
 //           [--sphere cx cy cz r]...      obstacle spheres of the collision scene (the CBspheres scenes hold two)
 //           [--tris file]                 obstacle triangles (int64 count, then p1 p2 p3 n1 n2 n3 as 18 doubles each)
+//           [--surface file]              after the last step: updateSurface() (marching cubes on the GPU), int64 count + 18 doubles
+//                                         per triangle (p1 p2 p3 n1 n2 n3), the layout of oracle/ref_harness --surface
 //           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
@@ -22,7 +24,7 @@ int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
   std::vector<double> spheres;
-  const char* trisfile = nullptr;
+  const char* trisfile = nullptr; const char* surffile = nullptr;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-p" && i + 1 < argc) pfile = argv[++i];
@@ -32,6 +34,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
     else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }   // obstacle sphere cx cy cz r, repeatable
     else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];            // obstacle triangles: int64 count + 18 doubles each
+    else if (a == "--surface" && i + 1 < argc) surffile = argv[++i];          // marching-cubes surface of the final state
     else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
     else if (a == "--load-state" && i + 1 < argc) load_state = argv[++i];   // continue from a restart file instead of -p
     else if (a == "--quiet") quiet = true;
@@ -96,6 +99,16 @@ int main(int argc, char** argv) {
     double per = done ? secs / done : 0.0;
     for (auto& st : frames) { fwrite(st.data(), 8, st.size(), f); fwrite(zero.data(), 4, n, f); fwrite(&per, 8, 1, f); }
     fclose(f);
+  }
+  if (surffile) {
+    ps->updateSurface();
+    FILE* sf = fopen(surffile, "wb");
+    if (!sf) { printf("[ERROR] cannot open %s\n", surffile); return EXIT_FAILURE; }
+    const int64_t nt = (int64_t)ps->surface.size();
+    fwrite(&nt, 8, 1, sf);
+    for (const Particles::SurfaceTriangle& t : ps->surface) fwrite(&t, sizeof(double), 18, sf);
+    fclose(sf);
+    fprintf(stderr, "including %lld marching cube surfacing triangles\n", (long long)nt);   // pathtracer.cpp:250
   }
   if (save_state && !ps->saveCheckpoint(save_state, &err)) { printf("[ERROR] %s\n", err.c_str()); return EXIT_FAILURE; }
   fprintf(stderr, "{\"n\": %lld, \"steps\": %d, \"seconds_total\": %.6f, \"ms_per_step_incl_readback\": %.4f}\n", (long long)n, done, secs,

@@ -91,3 +91,29 @@ def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
     # -d 0.05 => ceil(0.05/0.016) = 4 steps (while simulate_time < T, Q18)
     r = subprocess.run([exe, "-p", xml, "-d", "0.05", "--quiet"], capture_output=True, text=True)
     assert json.loads(r.stderr.strip().splitlines()[-1])["steps"] == 4
+
+
+@pytest.mark.gpu
+def test_cli_surface_equals_python_api(tmp_path):
+    """Particles::updateSurface of the host adapter (pbf_run --surface) == api.Solver.extract_surface on the same run,
+    and within the fixture's tolerance of the unmodified reference's surface of the same scene and step count."""
+    exe = _build()
+    fx = np.load(os.path.join(GOLDEN, "ref_surface_p.npz"))
+    sc = np.load(os.path.join(GOLDEN, "scene_p.npz"))
+    rho0, steps = float(sc["rho0"]), 3
+    xml = str(tmp_path / "p.xml"); sf = str(tmp_path / "surf.bin")
+    _write_xml(xml, sc["pos"], sc["vel"], rho0)
+    r = subprocess.run([exe, "-p", xml, "--steps", str(steps), "--surface", sf, "--quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(sf, dtype=np.uint8)
+    nt = int(raw[:8].view(np.int64)[0])
+    tris = raw[8:].view(np.float64).reshape(nt, 18)
+    assert f"including {nt} marching cube surfacing triangles" in r.stderr
+    from fluid_b200 import api
+    g = api.Solver(api.default_params(rest_density=rho0))
+    g.upload(sc["pos"], sc["vel"]); g.estimate_densities(); g.step(steps)
+    want = g.extract_surface(rho0)
+    assert tris.shape == want.shape and np.array_equal(tris, want)
+    assert nt > 500 and abs(nt - len(fx["tris"])) < 0.5 * len(fx["tris"])     # same scene, 3 vs 12 steps: same order of magnitude
+    nrm = np.linalg.norm(tris[:, 9:12], axis=1)
+    assert np.all((np.abs(nrm - 1) < 1e-9) | (nrm == 0))
