@@ -27,5 +27,16 @@ for dims in ((64, 32, 32), (400, 200, 200)):
         t0 = time.perf_counter(); do = o.density_at(q[:20000]); dtc = time.perf_counter() - t0
         row.update({"cpu_reference_algorithm_points_per_s": 20000 / dtc, "cpu_threads": H.oracle_lib().oracle_max_threads(),
                     "max_rel_err_vs_cpu": float(np.abs(d[:20000] - do).max() / do.max())})
+    # the whole surfacer on the device (pbf_extract_surface): lattice over the fluid's bounding box, step H/2, iso 0.95 rho0
+    slo, shi = tuple(float(v) for v in (P.min(0) - 0.3)), tuple(float(v) for v in (P.max(0) + 0.3))
+    g.extract_surface(700.0, lo=slo, hi=(slo[0] + 1.0, slo[1] + 1.0, slo[2] + 1.0))      # warm-up (table upload)
+    t0 = time.perf_counter(); tris = g.extract_surface(700.0, lo=slo, hi=shi); dts = time.perf_counter() - t0
+    cells = int(np.prod([int((shi[a] - slo[a]) / 0.15) + 1 for a in range(3)]))
+    row.update({"surface_lattice_cells": cells, "surface_triangles": len(tris), "surface_gpu_seconds_incl_readback": dts,
+                "surface_density_evaluations": 8 * cells + 18 * len(tris)})
+    if n <= 100000:
+        t0 = time.perf_counter(); ts = o.surface(700.0, lo=slo, hi=shi); dtc = time.perf_counter() - t0
+        row.update({"surface_cpu_reference_algorithm_seconds": dtc, "surface_same_triangle_count": bool(len(ts) == len(tris)),
+                    "surface_max_abs_diff_vs_cpu": float(np.abs(ts - tris).max()) if len(ts) == len(tris) else None})
     out.append(row)
 print(json.dumps(out, indent=1))
