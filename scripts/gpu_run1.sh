@@ -1,3 +1,3 @@
 set -x
-timeout 600 python scripts/density_field_bench.py > gpurun_out/r1_density_surface.json 2> gpurun_out/r1_density_surface.err; tail -40 gpurun_out/r1_density_surface.json; tail -5 gpurun_out/r1_density_surface.err
-( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r1_pytest_gpu.log 2>&1; tail -5 gpurun_out/r1_pytest_gpu.log
+python __graft_entry__.py --smoke > gpurun_out/r1_smoke.log 2>&1; tail -3 gpurun_out/r1_smoke.log
+( timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_small.py ) > gpurun_out/r1_sanitizer.txt 2>&1; tail -6 gpurun_out/r1_sanitizer.txt

@@ -14,4 +14,12 @@ os.environ["PBF_GRAPH"] = "0"
 g = api.Solver(api.default_params(rest_density=700.0)); g.upload(ref["pos"], ref["vel"]); g.step(2); g.download()
 s = slab.SlabSolver(api.default_params(rest_density=700.0), 0, 1)
 s.upload_local(ref["pos"], ref["vel"]); s.step(2); s.download_local(); s.neighbor_digest()
+# obstacle spheres + a triangle mesh through the device BVH, and the marching-cubes surfacer
+g = api.Solver(api.default_params(rest_density=700.0))
+keep = ref["pos"][:, 1] >= 0.75
+mesh = np.concatenate([H.uv_sphere_mesh((-0.5, 0.32, 0.5), 0.3, 16, 32), H.heightfield_mesh(-1.05, 1.05, -1.05, 1.05, 24, 24)])
+g.set_obstacle_triangles(mesh); g.set_obstacle_spheres(np.array([[0.5, 0.4, -0.5, 0.2]]))
+g.upload(ref["pos"][keep], ref["vel"][keep]); g.step(25)
+t = g.extract_surface(700.0); g.step(1); t2 = g.extract_surface(700.0, step=0.07)
+print("surface triangles", len(t), len(t2))
 print("sanitize run ok")
