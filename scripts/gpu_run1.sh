@@ -1,3 +1,2 @@
 set -x
-python __graft_entry__.py --smoke > gpurun_out/r1_smoke.log 2>&1; tail -3 gpurun_out/r1_smoke.log
-( timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_small.py ) > gpurun_out/r1_sanitizer.txt 2>&1; tail -6 gpurun_out/r1_sanitizer.txt
+( time timeout 400 python bench.py ) > gpurun_out/r1_bench_1gpu.json 2> gpurun_out/r1_bench_1gpu.err; tail -c 300 gpurun_out/r1_bench_1gpu.json; tail -5 gpurun_out/r1_bench_1gpu.err
