@@ -1,2 +1,2 @@
 set -x
-( time timeout 400 python bench.py ) > gpurun_out/r1_bench_1gpu.json 2> gpurun_out/r1_bench_1gpu.err; tail -c 300 gpurun_out/r1_bench_1gpu.json; tail -5 gpurun_out/r1_bench_1gpu.err
+( time timeout 900 python -m pytest tests -m gpu -x -q -k "edge_cases or obstacle_mesh" ) > gpurun_out/r1_pytest_new.log 2>&1; tail -30 gpurun_out/r1_pytest_new.log

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=12)
     ap.add_argument("--same-gpu", action="store_true")
     ap.add_argument("--spheres", action="store_true", help="obstacle spheres on the floor, one of them across a slab boundary")
+    ap.add_argument("--mesh", action="store_true", help="a tessellated sphere (device BVH) across the slab boundary")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -56,12 +57,21 @@ def main():
     for c in spheres:
         keep = np.linalg.norm(pos - c[:3], axis=1) > c[3] + 0.02
         pos, vel = pos[keep], vel[keep]
+    mesh = None
+    if args.mesh:
+        import helpers as H
+        mc = np.array([0.05 * nx + 0.13, 0.5, 0.05 * nz]); mr = 0.6
+        mesh = H.uv_sphere_mesh(mc, mr, 20, 40)
+        keep = np.linalg.norm(pos - mc, axis=1) > mr + 0.02
+        pos, vel = pos[keep], vel[keep]
     n = pos.shape[0]
     # rank r starts with the r-th contiguous chunk of the x-outer lattice order (roughly its slab)
     per = n // world
     lo = rank * per; hi = n if rank == world - 1 else (rank + 1) * per
     s = slab.SlabSolver(api.default_params(**prm), rank, world, device=local)
     s.set_obstacle_spheres(spheres)
+    if mesh is not None:
+        s.set_obstacle_triangles(mesh)
     s.upload_local(pos[lo:hi], vel[lo:hi], id_offset=lo)
     s.step(args.steps); s.sync()
     P, V, R, I, d, c = s.gather_all()
@@ -70,6 +80,8 @@ def main():
     if rank == 0:
         g = api.Solver(api.default_params(**prm), device=local)
         g.set_obstacle_spheres(spheres)
+        if mesh is not None:
+            g.set_obstacle_triangles(mesh)
         g.upload(pos, vel); g.step(args.steps)
         Pg, Vg, Rg = g.download()
         dg, cg = g.neighbor_digest()
@@ -81,6 +93,7 @@ def main():
             "max_dpos": float(np.abs(P - Pg).max()) if len(P) == len(Pg) else None,
             "avg_rho_slab": [a_first, a_final], "avg_rho_single": [a, b],
             "finite": bool(np.isfinite(P).all()),
+            "inside_mesh": int((np.linalg.norm(P - mc, axis=1) < mr * 0.99).sum()) if mesh is not None else None,
             "min_sphere_gap": float(min((np.linalg.norm(P - c[:3], axis=1).min() - c[3]) for c in spheres)) if len(spheres) else None,
         })
         print("SLAB_RESULT " + json.dumps(out), flush=True)

@@ -617,6 +617,36 @@ def test_surface_extraction_matches_reference_and_oracle(name):
     assert got3.shape == ref3.shape and len(got3) > 100 and np.abs(got3 - ref3).max() <= 1e-7
 
 
+def test_surface_and_mesh_api_edge_cases():
+    """Empty handles, partial buffers, bad lattices; hierarchies over 1, 5 and 200 identical / degenerate triangles."""
+    import ctypes as C
+    from fluid_b200 import api
+    g = _gpu(700.0)
+    assert g.extract_surface(700.0).shape == (0, 18)                       # nothing uploaded yet
+    ref = np.load(os.path.join(GOLDEN, "ref_jitter_two_blocks.npz"))
+    g.upload(ref["pos"], ref["vel"])
+    full = g.extract_surface(700.0)
+    assert len(full) > 100
+    lo = np.array([-1.0, 0.0, -1.0]); hi = np.array([1.0, 1.5, 1.0]); nt = C.c_size_t(0)
+    part = np.full((10, 18), np.nan)
+    g._ck(g.lib.pbf_extract_surface(g.h, lo.ctypes.data, hi.ctypes.data, 0.95 * 700.0, 0.15, 0.001, 10, part.ctypes.data, C.byref(nt)))
+    assert nt.value == len(full) and np.array_equal(part, full[:10])       # cap < count: the first cap triangles, full count reported
+    for bad in (dict(step=0.0), dict(step=float("nan")), dict(lo=(1.0, 0.0, -1.0), hi=(-1.0, 1.5, 1.0)), dict(step=1e-9)):
+        with pytest.raises(api.PbfError):
+            g.extract_surface(700.0, **bad)
+    assert np.array_equal(g.extract_surface(700.0), full)                  # the handle is still usable, same answer
+    # hierarchies: one triangle, five (inner root), 200 copies of one (all centroids equal), zero-area triangles
+    tri = H.box_mesh((-0.7, 0.0, -0.7), (-0.2, 0.4, -0.2))
+    deg = tri[:3].copy(); deg[:, 3:9] = deg[:, 0:3].repeat(1, axis=0).reshape(3, 3)[:, [0, 1, 2, 0, 1, 2]]
+    for mesh in (tri[:1], tri[:5], np.tile(tri[:1], (200, 1)), np.concatenate([deg, tri])):
+        a = _gpu(700.0, iterations=2); a.set_obstacle_triangles(mesh); a.upload(ref["pos"], ref["vel"]); a.step(3)
+        o = _oracle(700.0, 32, iterations=2); o.set_triangles(mesh); o.upload(ref["pos"], ref["vel"]); o.step(2)
+        b = _gpu(700.0, iterations=2); b.set_obstacle_triangles(mesh); b.capture(True); b.upload(*o.download()[:2]); b.step(1)
+        o.step(1)
+        assert np.array_equal(b.array(ARRAY_XPRED), o.array(ARRAY_XPRED)), len(mesh)
+        assert np.isfinite(a.download()[0]).all()
+
+
 def test_graph_replay_equals_plain_launches(monkeypatch):
     """Launch-bound scenes replay the step as a CUDA graph (one per buffer parity, PBF_GRAPH): the state after
     7 steps, a re-upload and 3 more steps is bit-identical to plain launches, and launch_count() still counts

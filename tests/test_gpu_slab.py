@@ -54,6 +54,13 @@ def test_two_slabs_with_obstacle_spheres():
     assert -2e-6 <= res["min_sphere_gap"] <= 1e-3, res["min_sphere_gap"]     # particles rest on the spheres, none inside
 
 
+def test_two_slabs_with_obstacle_mesh():
+    """A 1520-triangle obstacle mesh (device BVH) across the slab boundary: every rank holds the whole hierarchy."""
+    res = _run(2, ["--backend", "gloo", "--same-gpu", "--steps", "6", "--mesh"], 29617)
+    _check(res)
+    assert res["inside_mesh"] == 0
+
+
 def test_three_slabs_shared_gpu_gloo():
     """Three ranks: the middle slab has neighbours on both sides."""
     _check(_run(3, ["--backend", "gloo", "--same-gpu", "--steps", "5", "--dims", "120", "16", "16"], 29612))
