@@ -1,2 +1,2 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -x -q -k "edge_cases or obstacle_mesh" ) > gpurun_out/r1_pytest_new.log 2>&1; tail -30 gpurun_out/r1_pytest_new.log
+( time timeout 600 python bench.py --block 3200 200 200 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e ) > gpurun_out/r1_bench_1gpu_128m.json 2> gpurun_out/r1_bench_1gpu_128m.err; tail -c 300 gpurun_out/r1_bench_1gpu_128m.json; tail -5 gpurun_out/r1_bench_1gpu_128m.err
