@@ -1,2 +1,4 @@
 set -x
-( time timeout 600 python bench.py --block 3200 200 200 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e ) > gpurun_out/r1_bench_1gpu_128m.json 2> gpurun_out/r1_bench_1gpu_128m.err; tail -c 300 gpurun_out/r1_bench_1gpu_128m.json; tail -5 gpurun_out/r1_bench_1gpu_128m.err
+PBF_TEX=0 timeout 200 python scripts/quick_bench.py 400 200 200 3 > gpurun_out/r1_qb_tex0.json 2>&1
+PBF_TEX=1 timeout 200 python scripts/quick_bench.py 400 200 200 3 > gpurun_out/r1_qb_tex1.json 2>&1
+grep -h -A1 "\"lambda\"\|\"ms_per_step\":\|avg_rho" gpurun_out/r1_qb_tex0.json gpurun_out/r1_qb_tex1.json | grep -v "^--"
