@@ -277,7 +277,7 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
                   const float4* __restrict__ xs,
                   const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ nbr,
                   uint32_t* __restrict__ slice_off, uint32_t* __restrict__ nbr_cnt,
-                  unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc) {
+                  unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc, int use_per_lane) {
   const uint32_t t = blockIdx.x * TPB + threadIdx.x;     // index inside the owned range
   const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
@@ -290,6 +290,52 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   if (valid) {
     pi = xyz(xs[i]);
     c = cell_coords(P, pi.x, pi.y, pi.z);
+  }
+  // Warp-uniform evaluation: when all particles of the warp sit in the same (x, y) cell column (all but the one warp in
+  // ~56 that straddles two columns), their candidate ranges of a z-run are shifted copies of each other, so the warp
+  // walks the UNION of the 32 ranges together: 32 candidates per step are loaded once, coalesced, parked in shared
+  // memory and read back as broadcasts, and every lane tests every one of them against its own particle.  Candidates
+  // outside a lane's own (conservative) range cannot be neighbours, so the exact predicate alone yields the same
+  // bits; all 32 lanes stay busy for the same number of steps.  Only non-zero words are kept.
+  __shared__ float4 stage[TPB / 32][32];
+  const int wid = threadIdx.x >> 5;
+  const int col = valid ? c.x * P.gdim[1] + c.y : -1;
+  const int col0 = __shfl_sync(0xffffffffu, col, 0);
+  bool uniform = __all_sync(0xffffffffu, !valid || col == col0) != 0 && !use_per_lane;
+  if (uniform) {
+#pragma unroll 1
+    for (int k = 0; k < 9; k++) {
+      uint32_t b0 = 0, e0 = 0;
+      if (valid) nb_run_range(P, cell_start, pi, c, k, cell, b0, e0);
+      const bool has = e0 > b0;
+      const uint32_t ub = __reduce_min_sync(0xffffffffu, has ? b0 : 0xffffffffu), ue = __reduce_max_sync(0xffffffffu, has ? e0 : 0u);
+      for (uint32_t wb = ub; wb < ue; wb += 32u) {
+        const uint32_t lim = min(32u, ue - wb);
+        stage[wid][lane] = (uint32_t)lane < lim ? __ldg(xs + wb + lane) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        __syncwarp();
+        uint32_t m = 0;
+        for (uint32_t g = 0; g < lim; g += 8) {
+          uint32_t m8 = 0;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const float4 q = stage[wid][g + u];
+            if (ex_is_neighbor(pi, make_float3(q.x, q.y, q.z), P.h2)) m8 |= (1u << u);
+          }
+          m |= m8 << g;
+        }
+        __syncwarp();
+        if (!include_self && i - wb < 32u) m &= ~(1u << (i - wb));      // only the own column's run contains i
+        if (!valid) m = 0;
+        if (m) {
+          cnt += __popc(m);
+          if (nwords < (uint32_t)NB_TOTW) { masks[nwords] = m; wbase[nwords] = wb; cnt_cached = cnt; }
+          nwords++;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, nwords > (uint32_t)NB_TOTW)) { uniform = false; cnt = 0; nwords = 0; cnt_cached = 0; }   // crowded: per-lane path below
+  }
+  if (!uniform && valid) {
 #pragma unroll 1
     for (int k = 0; k < 9; k++) {
       uint32_t b0, e0;
@@ -832,13 +878,19 @@ void enqueue_sort(Solver* h, size_t n_in) {
   h->cur = nxt;
 }
 
+static int nb_per_lane() {      // PBF_NB_PER_LANE=1: the per-lane candidate walk for every warp (A/B and fallback testing)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PBF_NB_PER_LANE"); v = (e && atoi(e)) ? 1 : 0; }
+  return v;
+}
+
 // Phase 3: frozen neighbour lists for the range [r_i0, r_i0 + r_cnt) of the n_sorted sorted particles.
 void enqueue_build(Solver* h, int include_self) {
   h->prof_begin(K_REORDER);
   k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega, h->xv);
   h->prof_end(K_REORDER); h->launches++;
   LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
-         h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc);
+         h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc, nb_per_lane());
 }
 
 // Sub-ranges of the owned range for overlapping halo exchange with compute (slab mode):

@@ -1,5 +1,4 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -q ) > gpurun_out/r1_pytest_gpu.log 2>&1; tail -6 gpurun_out/r1_pytest_gpu.log
-python __graft_entry__.py --smoke 2>&1 | tail -1
-( time timeout 400 python bench.py ) > gpurun_out/r1_bench_1gpu.json 2> gpurun_out/r1_bench_1gpu.err; tail -c 200 gpurun_out/r1_bench_1gpu.json
-( timeout 300 python bench.py --impl reference --steps 5 --warmup 1 ) > gpurun_out/r1_bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/r1_bench_reference.json
+PBF_NB_PER_LANE=0 timeout 200 python scripts/quick_bench.py 400 200 200 3 > gpurun_out/r1_qb_nb_uni2.json 2>&1
+grep -A2 '"build_neighbors"' gpurun_out/r1_qb_nb_uni2.json; grep '"ms_per_step":\|mean_nbrs' gpurun_out/r1_qb_nb_uni2.json | grep -v "   "
+( time timeout 900 python -m pytest tests -m gpu -x -q -k "neighbor or crowded or capacity or large_block" ) > gpurun_out/r1_pytest_nb.log 2>&1; tail -3 gpurun_out/r1_pytest_nb.log
