@@ -294,10 +294,10 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   // Warp-uniform evaluation: when all particles of the warp sit in the same (x, y) cell column (all but the one warp in
   // ~56 that straddles two columns), their candidate ranges of a z-run are shifted copies of each other, so the warp
   // walks the UNION of the 32 ranges together: 32 candidates per step are loaded once, coalesced, parked in shared
-  // memory and read back as broadcasts, and every lane tests every one of them against its own particle.  Candidates
+  // memory (coordinate-major) and read back as 128-bit broadcasts of 4 candidates' x, y or z, and every lane tests every one of them against its own particle.  Candidates
   // outside a lane's own (conservative) range cannot be neighbours, so the exact predicate alone yields the same
   // bits; all 32 lanes stay busy for the same number of steps.  Only non-zero words are kept.
-  __shared__ float4 stage[TPB / 32][32];
+  __shared__ __align__(16) float stage[TPB / 32][3][32];
   const int wid = threadIdx.x >> 5;
   const int col = valid ? c.x * P.gdim[1] + c.y : -1;
   const int col0 = __shfl_sync(0xffffffffu, col, 0);
@@ -311,16 +311,25 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
       const uint32_t ub = __reduce_min_sync(0xffffffffu, has ? b0 : 0xffffffffu), ue = __reduce_max_sync(0xffffffffu, has ? e0 : 0u);
       for (uint32_t wb = ub; wb < ue; wb += 32u) {
         const uint32_t lim = min(32u, ue - wb);
-        stage[wid][lane] = (uint32_t)lane < lim ? __ldg(xs + wb + lane) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        {
+          const float4 q = (uint32_t)lane < lim ? __ldg(xs + wb + lane) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+          stage[wid][0][lane] = q.x; stage[wid][1][lane] = q.y; stage[wid][2][lane] = q.z;
+        }
         __syncwarp();
         uint32_t m = 0;
-        for (uint32_t g = 0; g < lim; g += 8) {
+        for (uint32_t g = 0; g < lim; g += 8) {       // coordinate-major staging: one 128-bit broadcast read brings 4 candidates' x (y, z)
+          const float4 xa = *reinterpret_cast<const float4*>(&stage[wid][0][g]), xb = *reinterpret_cast<const float4*>(&stage[wid][0][g + 4]);
+          const float4 ya = *reinterpret_cast<const float4*>(&stage[wid][1][g]), yb = *reinterpret_cast<const float4*>(&stage[wid][1][g + 4]);
+          const float4 za = *reinterpret_cast<const float4*>(&stage[wid][2][g]), zb = *reinterpret_cast<const float4*>(&stage[wid][2][g + 4]);
           uint32_t m8 = 0;
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const float4 q = stage[wid][g + u];
-            if (ex_is_neighbor(pi, make_float3(q.x, q.y, q.z), P.h2)) m8 |= (1u << u);
-          }
+          if (ex_is_neighbor(pi, make_float3(xa.x, ya.x, za.x), P.h2)) m8 |= 1u;
+          if (ex_is_neighbor(pi, make_float3(xa.y, ya.y, za.y), P.h2)) m8 |= 2u;
+          if (ex_is_neighbor(pi, make_float3(xa.z, ya.z, za.z), P.h2)) m8 |= 4u;
+          if (ex_is_neighbor(pi, make_float3(xa.w, ya.w, za.w), P.h2)) m8 |= 8u;
+          if (ex_is_neighbor(pi, make_float3(xb.x, yb.x, zb.x), P.h2)) m8 |= 16u;
+          if (ex_is_neighbor(pi, make_float3(xb.y, yb.y, zb.y), P.h2)) m8 |= 32u;
+          if (ex_is_neighbor(pi, make_float3(xb.z, yb.z, zb.z), P.h2)) m8 |= 64u;
+          if (ex_is_neighbor(pi, make_float3(xb.w, yb.w, zb.w), P.h2)) m8 |= 128u;
           m |= m8 << g;
         }
         __syncwarp();
