@@ -1,3 +1,2 @@
 set -x
-( time timeout 900 python -m pytest tests -m gpu -q ) > gpurun_out/r1_pytest_gpu.log 2>&1; tail -6 gpurun_out/r1_pytest_gpu.log
-( time timeout 400 python bench.py ) > gpurun_out/r1_bench_1gpu.json 2> gpurun_out/r1_bench_1gpu.err; tail -c 200 gpurun_out/r1_bench_1gpu.json
+timeout 600 python scripts/c3_1m.py > gpurun_out/r1_c3_1m.json 2> gpurun_out/r1_c3_1m.err; cat gpurun_out/r1_c3_1m.json; tail -3 gpurun_out/r1_c3_1m.err
