@@ -1,2 +1,3 @@
 set -x
-timeout 600 python scripts/c3_1m.py > gpurun_out/r1_c3_1m.json 2> gpurun_out/r1_c3_1m.err; cat gpurun_out/r1_c3_1m.json; tail -3 gpurun_out/r1_c3_1m.err
+PBF_SMEM=1 timeout 200 python scripts/quick_bench.py 400 200 200 3 > gpurun_out/r1_qb_smem2.json 2> gpurun_out/r1_qb_smem2.err
+grep -A2 '"lambda"' gpurun_out/r1_qb_smem2.json; grep PBF_SMEM gpurun_out/r1_qb_smem2.err; grep avg_rho -A2 gpurun_out/r1_qb_smem2.json
