@@ -205,14 +205,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # one rank per GPU: keep the rank (and the page-locked host buffers of the e2e leg, which are placed where the
-        # thread that locks them runs) on the CPU socket its GPU hangs off
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-        except Exception as e:   # affinity is an optimisation of the e2e leg only
-            print(f"bench.py: no CPU affinity ({e})", file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nx, ny, nz = args.block or BLOCK_PER_GPU
     iters = args.iterations
