@@ -289,6 +289,55 @@ def test_large_block_properties():
     _gate_whole_step("24^3 block", Pg, Rg, Po, Ro, 700.0, p50_gate=max(1e-5, floor))
 
 
+def test_full_size_c4_properties():
+    """The bench workload itself (BASELINE config C4: 400 x 200 x 200 = 16M particles, box (120, 30, 20.1)), two steps:
+    neighbour relation symmetric (sum_i digest_i == sum_j count_j * mix64(j)), interior counts inside the lattice's
+    analytic range, state finite and inside the box, mean density relaxing towards rho0, the step deterministic, and
+    the 1M sub-problem that shares its corner reproduced bit for bit by a separate 1M run where the two cannot differ
+    (one step carries influence 26 neighbour hops = 7.8 far: 12 x (lambda, delta-p) + vorticity + confinement)."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~20 GB of device memory")
+    from fluid_b200 import api
+    nx, ny, nz = 400, 200, 200
+    pos, vel = lattice_block(nx, ny, nz, jitter=0.001, seed=1234)
+    box_min, box_max = (0.0, 0.0, 0.0), (120.0, 30.0, 20.1)
+    prm = dict(rest_density=700.0, box_min=box_min, box_max=box_max, y_light=30.0, z_front=20.1)
+    g = api.Solver(api.default_params(**prm))
+    g.upload(pos, vel); g.step(1)
+    dg, cg = g.neighbor_digest()
+    j = np.arange(len(cg), dtype=np.uint64)
+    z = j + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    mix = z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        assert dg.sum(dtype=np.uint64) == (mix * cg.astype(np.uint64)).sum(dtype=np.uint64)
+    interior = cg.reshape(nx, ny, nz)[5:-5, 5:-5, 5:-5]
+    assert interior.min() >= 92 and interior.max() <= 122 and abs(interior.mean() - 107.0) < 0.5
+    a1, b1, _ = g.stats()
+    P1, _, R1 = g.download()
+    g.step(1)
+    a2, b2, _ = g.stats()
+    P, V, R = g.download()
+    assert np.isfinite(P).all() and np.isfinite(V).all() and np.isfinite(R).all()
+    assert (P >= np.array(box_min)).all() and (P <= np.float32(box_max).astype(np.float64)).all()
+    assert a1 > 900.0 and abs(b1 - 700.0) < 10.0 and abs(b2 - 700.0) < 10.0       # ~936 on the compressed lattice (no self term) -> rho0
+    g2 = api.Solver(api.default_params(**prm)); g2.upload(pos, vel); g2.step(2)
+    P2, V2, R2 = g2.download()
+    assert np.array_equal(P, P2) and np.array_equal(V, V2) and np.array_equal(R, R2)
+    # the 100^3 corner block run on its own: identical input particles in the same relative order on the same global
+    # grid; after ONE step particles further than 26 hops x 0.3 from the cut faces (x, y, z = 10) cannot have felt it
+    sel = np.zeros((nx, ny, nz), dtype=bool); sel[:100, :100, :100] = True
+    idx = np.flatnonzero(sel.reshape(-1))
+    gs = api.Solver(api.default_params(**prm)); gs.upload(pos[idx], vel[idx]); gs.step(1)
+    Ps, Vs, Rs = gs.download()
+    deep = np.all(pos[idx] < 2.0, axis=1)
+    assert deep.sum() > 6000
+    assert np.array_equal(Ps[deep], P1[idx][deep]) and np.array_equal(Rs[deep], R1[idx][deep])
+    assert not np.array_equal(Ps, P1[idx])                     # ... while the particles near the cut do differ
+
+
 def test_crowded_cells_neighbor_sets(monkeypatch):
     """Strong local compression: several hundred particles in a few cells, so that a z-run of 3
     cells holds more candidates than the neighbour build caches (6 words = 192): the tail words are
