@@ -558,6 +558,32 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   return PBF_OK;
 }
 
+// Pure host function (no device needed): the hierarchy pbf_set_obstacle_triangles would build over these triangles,
+// WITHOUT the safety margin on the node boxes.  nodes_out: 8 floats per node = lo.xyz, a (int bits), hi.xyz, b (int bits);
+// order_out: leaf order -> original triangle index.  Returns PBF_ERR_CAPACITY when cap_nodes is too small (n_nodes is set).
+int pbf_debug_build_bvh(size_t count, const double* q, float* nodes_out, size_t cap_nodes, uint32_t* order_out, size_t* n_nodes, int* depth) {
+  if (!q || !n_nodes || !depth || count == 0 || count > PBF_MAX_TRIANGLES) return PBF_ERR_INVALID;
+  std::vector<float> tb(9 * count);
+  for (size_t k = 0; k < count; k++) {
+    float* b = &tb[9 * k];
+    for (int a = 0; a < 3; a++) {
+      const float v0 = (float)q[18 * k + a], v1 = (float)q[18 * k + 3 + a], v2 = (float)q[18 * k + 6 + a];
+      b[a] = std::min(v0, std::min(v1, v2)); b[3 + a] = std::max(v0, std::max(v1, v2)); b[6 + a] = 0.5f * (b[a] + b[3 + a]);
+    }
+  }
+  BvhBuild B(tb);
+  B.order.resize(count);
+  for (size_t k = 0; k < count; k++) B.order[k] = (uint32_t)k;
+  B.nodes.reserve(8 * (count + 1));
+  B.nodes.resize(8);
+  B.build(0, 0, (uint32_t)count, 1);
+  *n_nodes = B.nodes.size() / 8; *depth = B.max_depth;
+  if (*n_nodes > cap_nodes || !nodes_out || !order_out) return PBF_ERR_CAPACITY;
+  std::memcpy(nodes_out, B.nodes.data(), B.nodes.size() * sizeof(float));
+  std::memcpy(order_out, B.order.data(), count * sizeof(uint32_t));
+  return PBF_OK;
+}
+
 int pbf_sync(pbf_handle* h) {
   if (!h) return PBF_ERR_INVALID;
   return sync_and_check(h);

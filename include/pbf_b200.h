@@ -149,6 +149,12 @@ enum { PBF_ARRAY_XSTAR = 0 /*n*3 predicted/corrected positions*/, PBF_ARRAY_LAMB
 int  pbf_debug_download_array(pbf_handle* h, int which, double* out);
 /* Keep a copy of x* right after predict+collide (PBF_ARRAY_XPRED) during subsequent steps. */
 int  pbf_debug_capture(pbf_handle* h, int on);
+/* Host only (no device): the bounding-volume hierarchy pbf_set_obstacle_triangles builds over these triangles, without the
+ * safety margin on the node boxes.  8 floats per node: lo.xyz, a, hi.xyz, b with the integers a, b stored as bits; a leaf
+ * (b > 0) holds triangles [a, a + b) of the leaf order, an inner node (b = 0) has its children at a and a + 1.
+ * order_out maps the leaf order to original triangle indices.  PBF_ERR_CAPACITY when cap_nodes is too small. */
+int  pbf_debug_build_bvh(size_t count, const double* p1_p2_p3_n1_n2_n3, float* nodes_out, size_t cap_nodes, uint32_t* order_out,
+                         size_t* n_nodes, int* depth);
 /* Number of kernel launches issued by this handle so far (bench "gpu_launches"). */
 uint64_t pbf_launch_count(pbf_handle* h);
 /* Per-kernel device time (CUDA events) accumulated since the last reset; names are static.

@@ -85,3 +85,48 @@ def test_grid_dims_and_columns_on_host():
     col = np.empty(5, dtype=np.int32)
     assert lib.pbf_cell_columns(C.byref(p), 5, x.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p)) == 0
     assert list(col) == [0, 0, 1, int(np.floor(np.float32(119.99) / cell)), dims[0] - 1]
+
+
+def test_obstacle_hierarchy_build_on_host():
+    """pbf_debug_build_bvh (pure host): the hierarchy pbf_set_obstacle_triangles hands to the device.  Every triangle
+    sits in exactly one leaf of at most 4, every node's box contains the boxes of its whole subtree, children are
+    adjacent, and the depth stays far below the traversal stack (40) — also for 5000 identical triangles."""
+    import helpers as H
+    from fluid_b200 import api
+    lib = api.load_library()
+    lib.pbf_debug_build_bvh.restype = C.c_int
+    lib.pbf_debug_build_bvh.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    mesh = np.concatenate([H.uv_sphere_mesh((-0.5, 0.32, 0.5), 0.3, 24, 48), H.heightfield_mesh(-1.05, 1.05, -1.05, 1.05, 40, 40)])
+    mesh = mesh[rng.permutation(len(mesh))]
+    cases = {"mixed": mesh, "one": mesh[:1], "five": mesh[:5], "identical": np.tile(mesh[:1], (5000, 1))}
+    for name, tris in cases.items():
+        tris = np.ascontiguousarray(tris, dtype=np.float64)
+        n = len(tris)
+        nodes = np.empty((2 * n + 8, 8), dtype=np.float32); order = np.empty(n, dtype=np.uint32)
+        nn = C.c_size_t(); depth = C.c_int()
+        assert lib.pbf_debug_build_bvh(n, tris.ctypes.data, nodes.ctypes.data, len(nodes), order.ctypes.data, C.byref(nn), C.byref(depth)) == 0, name
+        nodes = nodes[:nn.value]
+        ia = nodes[:, 3].copy().view(np.int32); ib = nodes[:, 7].copy().view(np.int32)
+        assert sorted(order.tolist()) == list(range(n)), name
+        assert depth.value <= 2 + int(np.ceil(np.log2(max(n, 2)))) and depth.value <= 40, (name, depth.value)
+        v = tris[:, :9].reshape(n, 3, 3).astype(np.float32)
+        tlo, thi = v.min(axis=1), v.max(axis=1)
+        seen = np.zeros(n, dtype=int)
+
+        def check(node, lo, hi):                      # returns the box of the subtree, asserts containment on the way
+            a, b = int(ia[node]), int(ib[node])
+            nlo, nhi = nodes[node, 0:3], nodes[node, 4:7]
+            assert np.all(nlo >= lo) and np.all(nhi <= hi), name
+            if b > 0:
+                assert b <= 4
+                ids = order[a:a + b]; seen[ids] += 1
+                assert np.all(tlo[ids] >= nlo) and np.all(thi[ids] <= nhi), name
+                return
+            assert 0 < a and a + 1 < len(nodes)
+            check(a, nlo, nhi); check(a + 1, nlo, nhi)
+        check(0, np.full(3, -np.inf, dtype=np.float32), np.full(3, np.inf, dtype=np.float32))
+        assert np.all(seen == 1), name
+    nn = C.c_size_t(); depth = C.c_int()
+    assert lib.pbf_debug_build_bvh(len(mesh), np.ascontiguousarray(mesh).ctypes.data, None, 0, None, C.byref(nn), C.byref(depth)) == api.PBF_ERR_CAPACITY
+    assert nn.value > len(mesh) // 4
