@@ -69,7 +69,7 @@ struct Particles {
   // GPU step takes the box (PbfParams) and the StaticScene::Sphere primitives: rows (cx, cy, cz, r), at most
   // PBF_MAX_SPHERES.  May be called at any time; takes effect from the next timeStep().
   void setObstacleSpheres(const std::vector<double>& cx_cy_cz_r);
-  // ... and its triangle primitives (small meshes): 18 doubles each, p1 p2 p3 n1 n2 n3 (pbf_set_obstacle_triangles)
+  // ... and its triangle primitives (meshes up to 2^22 triangles, device BVH): 18 doubles each, p1 p2 p3 n1 n2 n3 (pbf_set_obstacle_triangles)
   void setObstacleTriangles(const std::vector<double>& p1_p2_p3_n1_n2_n3);
   // Marching-cubes surface on the GPU (pbf_extract_surface): same triangles, same order as the reference's
   // getSurfacePrims (particles.cpp:352-391) / updateSurface (393-402: isolevel 0.95 rho0, step 0.5 H)
