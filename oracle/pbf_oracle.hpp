@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -109,7 +110,7 @@ struct Oracle {
     YL = R(p.y_light); ZF = R(p.z_front);
     // fp32 contact rules of the obstacle triangles scale with the resolution of a coordinate (see mesh_hit_onesided)
     SKIN = TOL_N = R(0); TOL_RAY = R(0);
-    if (sizeof(R) == 4) {
+    if (sizeof(R) == 4 && !std::getenv("PBF_ORACLE_NO_FP32_CONTACT_RULES")) {   // the switch exists for the test that shows what they are for
       double m = 0;
       for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs((double)p.box_min[a]), std::fabs((double)p.box_max[a])));
       const double ulp = m * 1.1920928955078125e-07;

@@ -233,3 +233,43 @@ def test_surface_matches_reference_fixture(name):
     got = o.surface(rho0)
     assert got.shape == want.shape, (got.shape, want.shape)
     assert np.array_equal(got, want), f"{int(np.any(got != want, axis=1).sum())} triangles differ, max {np.abs(got - want).max():.3e}"
+
+
+@pytest.mark.parametrize("offset", [0.0, 100.0])
+def test_fp32_triangle_contact_rules_do_not_leak(offset):
+    """The fp32-only contact rules of the one-sided triangles (rest a skin in front of the plane, hold what is a hair
+    behind it; oracle/pbf_oracle.hpp mesh_hit_onesided) exist because fp32 cannot resolve the reference's 1e-11
+    stand-off: without them 637 of 41k particles sat inside a tessellated sphere after 5 steps at |x| ~ 100, and a few
+    even at the origin.  With them nothing is inside the polyhedron, at the origin and at |x| ~ 100 (one ulp = 8e-6)
+    alike, and fp64 (which never leaked) agrees.  The GPU reproduces the fp32 oracle's x* bit for bit
+    (tests/test_gpu_parity.py), so this is also its guarantee."""
+    from helpers import lattice_block, uv_sphere_mesh
+    pos, vel = lattice_block(30, 24, 30, origin=(offset + 0.1, 0.1, offset + 0.1), jitter=0.001)
+    c = np.array([offset + 1.5, 0.0, offset + 1.5]); r = 1.0
+    keep = np.linalg.norm(pos - c, axis=1) > r + 0.02
+    pos, vel = pos[keep], vel[keep]
+    tris = uv_sphere_mesh(c, r, 16, 32)
+    e1 = tris[:, 3:6] - tris[:, 0:3]; e2 = tris[:, 6:9] - tris[:, 0:3]
+    ng = np.cross(e1, e2); ng /= np.linalg.norm(ng, axis=1)[:, None]
+
+    def inside(P):                                   # particles strictly inside the convex polyhedron, by more than 1e-4
+        near = np.flatnonzero(np.linalg.norm(P - c, axis=1) < r * 1.0005)
+        if len(near) == 0:
+            return 0
+        sd = np.einsum("pfk,fk->pf", P[near][:, None, :] - tris[None, :, 0:3], ng).max(axis=1)
+        return int((sd < -1e-4).sum())
+    prm = default_params(rest_density=700.0, xsph_mode=XSPH_JACOBI, box_min=(offset, 0, offset), box_max=(offset + 9, 12, offset + 3.1),
+                         y_light=12.0, z_front=offset + 3.1)
+    for prec in (32, 64):
+        o = Oracle(prm, prec, COLLIDE_BOX, SEARCH_GRID); o.set_triangles(tris); o.upload(pos, vel)
+        for _ in range(4):
+            o.step(1)
+            assert inside(o.download()[0]) == 0, (offset, prec)
+    if offset > 0:                                   # and without the rules the fp32 oracle does leak there
+        os.environ["PBF_ORACLE_NO_FP32_CONTACT_RULES"] = "1"
+        try:
+            o = Oracle(prm, 32, COLLIDE_BOX, SEARCH_GRID); o.set_triangles(tris); o.upload(pos, vel)
+        finally:
+            del os.environ["PBF_ORACLE_NO_FP32_CONTACT_RULES"]
+        o.step(4)
+        assert inside(o.download()[0]) > 0
