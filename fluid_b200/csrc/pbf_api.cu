@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "pbf_internal.h"
@@ -484,6 +485,23 @@ struct BvhBuild {
     build(left + 1, first + half, count - half, depth + 1);
   }
 };
+// fp32 bounding boxes and centroids of the triangles (9 floats each: lo, hi, centre) and the hierarchy over them
+static void bvh_over_triangles(size_t count, const double* q, std::vector<float>& tb, BvhBuild*& out) {
+  tb.resize(9 * count);
+  for (size_t k = 0; k < count; k++) {
+    float* b = &tb[9 * k];
+    for (int a = 0; a < 3; a++) {
+      const float v0 = (float)q[18 * k + a], v1 = (float)q[18 * k + 3 + a], v2 = (float)q[18 * k + 6 + a];
+      b[a] = std::min(v0, std::min(v1, v2)); b[3 + a] = std::max(v0, std::max(v1, v2)); b[6 + a] = 0.5f * (b[a] + b[3 + a]);
+    }
+  }
+  out = new BvhBuild(tb);
+  out->order.resize(count);
+  for (size_t k = 0; k < count; k++) out->order[k] = (uint32_t)k;
+  out->nodes.reserve(8 * (count + 1));
+  out->nodes.resize(8);
+  out->build(0, 0, (uint32_t)count, 1);
+}
 }  // namespace
 
 // Obstacle triangles.  Edges, orientation and |e1 x e2| are precomputed in fp32 with the same single roundings as
@@ -501,7 +519,7 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
   h->dp.n_tri = 0; h->dp.tri = nullptr; h->dp.bvh = nullptr; h->dp.tri_id = nullptr;
   update_obstacle_box(h);
   if (count == 0) return PBF_OK;
-  std::vector<float> t(20 * count), tb(9 * count);
+  std::vector<float> t(20 * count), tb;
   float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
   for (size_t k = 0; k < count; k++) {
     volatile float v[18];
@@ -522,20 +540,12 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
     for (int a = 0; a < 9; a++) o[9 + a] = v[9 + a];
     o[18] = dsum < 0.f ? -1.f : 1.f;                    // orientation of e1 x e2 against the vertex normals
     o[19] = std::sqrt((float)qs);                       // |e1 x e2|
-    float* b = &tb[9 * k];
-    for (int a = 0; a < 3; a++) {
-      b[a] = std::min((float)v[a], std::min((float)v[3 + a], (float)v[6 + a]));
-      b[3 + a] = std::max((float)v[a], std::max((float)v[3 + a], (float)v[6 + a]));
-      b[6 + a] = 0.5f * (b[a] + b[3 + a]);
-      lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[3 + a]);
-    }
+    for (int p3 = 0; p3 < 3; p3++) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], (float)v[3 * p3 + a]); hi[a] = std::max(hi[a], (float)v[3 * p3 + a]); }
   }
-  BvhBuild B(tb);
-  B.order.resize(count);
-  for (size_t k = 0; k < count; k++) B.order[k] = (uint32_t)k;
-  B.nodes.reserve(8 * (count + 1));
-  B.nodes.resize(8);
-  B.build(0, 0, (uint32_t)count, 1);
+  BvhBuild* Bp = nullptr;
+  bvh_over_triangles(count, q, tb, Bp);
+  std::unique_ptr<BvhBuild> Bown(Bp);
+  BvhBuild& B = *Bp;
   if (B.max_depth > PBF_BVH_MAX_DEPTH) return fail(h, PBF_ERR_CAPACITY, "pbf_set_obstacle_triangles: hierarchy deeper than the traversal stack");
   const float margin = 1e-2f * h->dp.h + h->dp.tol_ray + 2.f * h->dp.skin;   // every accepted hit lies within tol_ray of the segment; plus the inflated edges and the rounding of a segment end
   for (size_t nd = 0; nd < B.nodes.size() / 8; nd++)
@@ -563,20 +573,11 @@ int pbf_set_obstacle_triangles(pbf_handle* h, size_t count, const double* q) {
 // order_out: leaf order -> original triangle index.  Returns PBF_ERR_CAPACITY when cap_nodes is too small (n_nodes is set).
 int pbf_debug_build_bvh(size_t count, const double* q, float* nodes_out, size_t cap_nodes, uint32_t* order_out, size_t* n_nodes, int* depth) {
   if (!q || !n_nodes || !depth || count == 0 || count > PBF_MAX_TRIANGLES) return PBF_ERR_INVALID;
-  std::vector<float> tb(9 * count);
-  for (size_t k = 0; k < count; k++) {
-    float* b = &tb[9 * k];
-    for (int a = 0; a < 3; a++) {
-      const float v0 = (float)q[18 * k + a], v1 = (float)q[18 * k + 3 + a], v2 = (float)q[18 * k + 6 + a];
-      b[a] = std::min(v0, std::min(v1, v2)); b[3 + a] = std::max(v0, std::max(v1, v2)); b[6 + a] = 0.5f * (b[a] + b[3 + a]);
-    }
-  }
-  BvhBuild B(tb);
-  B.order.resize(count);
-  for (size_t k = 0; k < count; k++) B.order[k] = (uint32_t)k;
-  B.nodes.reserve(8 * (count + 1));
-  B.nodes.resize(8);
-  B.build(0, 0, (uint32_t)count, 1);
+  std::vector<float> tb;
+  BvhBuild* Bp = nullptr;
+  bvh_over_triangles(count, q, tb, Bp);
+  std::unique_ptr<BvhBuild> Bown(Bp);
+  BvhBuild& B = *Bp;
   *n_nodes = B.nodes.size() / 8; *depth = B.max_depth;
   if (*n_nodes > cap_nodes || !nodes_out || !order_out) return PBF_ERR_CAPACITY;
   std::memcpy(nodes_out, B.nodes.data(), B.nodes.size() * sizeof(float));
