@@ -130,3 +130,98 @@ def test_obstacle_hierarchy_build_on_host():
     nn = C.c_size_t(); depth = C.c_int()
     assert lib.pbf_debug_build_bvh(len(mesh), np.ascontiguousarray(mesh).ctypes.data, None, 0, None, C.byref(nn), C.byref(depth)) == api.PBF_ERR_CAPACITY
     assert nn.value > len(mesh) // 4
+
+
+def test_hierarchy_walk_equals_scan_in_a_model_of_the_device_code():
+    """Model (numpy, fp64) of ex_mesh_hit / ex_tri_test (fluid_b200/csrc/pbf_device.cuh): the walk over the host-built
+    hierarchy, pruning with the SAME margin pbf_set_obstacle_triangles puts on the node boxes, must return the winner
+    of the scan over all triangles for every segment — including starts inside the contact skin, a hair behind a
+    plane, grazing directions and equally near hits on duplicated triangles (larger index wins).  This pins the
+    reasoning behind the margin (every accepted hit lies within tol_ray of the segment); the CUDA code itself is
+    checked bit for bit against the oracle's scan on the GPU (tests/test_gpu_parity.py)."""
+    import helpers as H
+    from fluid_b200 import api
+    lib = api.load_library()
+    lib.pbf_debug_build_bvh.restype = C.c_int
+    lib.pbf_debug_build_bvh.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    base = np.concatenate([H.uv_sphere_mesh((0.2, 0.5, -0.1), 0.4, 12, 24), H.heightfield_mesh(-1.0, 1.0, -1.0, 1.0, 16, 16)])
+    dup = base[rng.choice(len(base), 200, replace=False)]
+    tris = np.ascontiguousarray(np.concatenate([base, dup])[rng.permutation(len(base) + 200)], dtype=np.float64)
+    n = len(tris)
+    nodes = np.empty((2 * n + 8, 8), dtype=np.float32); order = np.empty(n, dtype=np.uint32)
+    nn = C.c_size_t(); depth = C.c_int()
+    assert lib.pbf_debug_build_bvh(n, tris.ctypes.data, nodes.ctypes.data, len(nodes), order.ctypes.data, C.byref(nn), C.byref(depth)) == 0
+    ia = nodes[:nn.value, 3].copy().view(np.int32); ib = nodes[:nn.value, 7].copy().view(np.int32)
+    nodes = nodes[:nn.value].astype(np.float64)
+    # the constants of fill_dev_params / pbf_set_obstacle_triangles for the default box (largest coordinate 1.49)
+    h = 0.3; ulp = 1.49 * 1.1920928955078125e-07
+    skin = max(1e-5 * h, 16 * ulp); tol_n = max(1e-4 * h, 64 * ulp) + skin; tol_ray = max(0.05 * h, 16 * max(1e-4 * h, 64 * ulp))
+    margin = 1e-2 * h + tol_ray + 2 * skin
+    nlo = nodes[:, 0:3] - margin - 1e-5 * np.abs(nodes[:, 0:3]); nhi = nodes[:, 4:7] + margin + 1e-5 * np.abs(nodes[:, 4:7])
+    p1 = tris[:, 0:3]; e1 = tris[:, 3:6] - p1; e2 = tris[:, 6:9] - p1
+    ng = np.cross(e1, e2); ngl = np.linalg.norm(ng, axis=1)
+    sg = np.where(np.einsum("ij,ij->i", ng, tris[:, 9:12] + tris[:, 12:15] + tris[:, 15:18]) < 0, -1.0, 1.0)
+    BT, TOL_T = 1e-6, 1e-4 * h
+
+    def tri_test(k, o, d, max_t, best):
+        s = o - p1[k]; s1 = np.cross(d, e2[k]); s2 = np.cross(s, e1[k]); dd = s1 @ e1[k]
+        if not (sg[k] * dd > 0):
+            return None
+        t = (s2 @ e2[k]) / dd
+        t -= min(skin * ngl[k] / abs(dd), tol_ray)
+        if t < 0:
+            if t >= -TOL_T or (t >= -tol_ray and -t * abs(dd) <= tol_n * ngl[k]):
+                t = 0.0
+            else:
+                return None
+        if t > max_t or (t == max_t and best >= 0 and k < best):
+            return None
+        u = (s1 @ s) / dd; v = (s2 @ d) / dd; w = 1 - u - v
+        if min(u, v, w) < -BT or max(u, v, w) > 1 + BT:
+            return None
+        return t
+
+    def scan(o, d, max_t):
+        best = -1
+        for k in range(n):
+            t = tri_test(k, o, d, max_t, best)
+            if t is not None:
+                max_t, best = t, k
+        return best, max_t
+
+    def walk(o, d, max_t):
+        best = -1; stack = [0]; visited = 0
+        while stack:
+            nd = stack.pop()
+            q = o + max_t * d
+            lo, hi = np.minimum(o, q), np.maximum(o, q)
+            if np.any(hi < nlo[nd]) or np.any(lo > nhi[nd]):
+                continue
+            if ib[nd] > 0:
+                for slot in range(ia[nd], ia[nd] + ib[nd]):
+                    k = int(order[slot]); visited += 1
+                    t = tri_test(k, o, d, max_t, best)
+                    if t is not None:
+                        max_t, best = t, k
+            else:
+                stack += [ia[nd] + 1, ia[nd]]
+        return best, max_t, visited
+    hits = contacts = 0; visited_total = 0; trials = 400
+    cen = (p1 + tris[:, 3:6] + tris[:, 6:9]) / 3; nh = (ng / ngl[:, None]) * sg[:, None]
+    for trial in range(trials):
+        k = int(rng.integers(n))
+        kind = trial % 4
+        off = [0.05, 0.5 * skin, -0.5 * tol_n, 0.02][kind]                    # far in front / inside the skin / a hair behind / near
+        noise = 0.01 * rng.normal(size=3) if kind != 3 else np.zeros(3)
+        if kind in (1, 2):
+            noise -= (noise @ nh[k]) * nh[k]                                    # stay at that distance from the plane
+        o = cen[k] + off * nh[k] + noise
+        d = -nh[k] + ([0.3, 0.3, 0.3, 30.0][kind]) * rng.normal(size=3)       # kind 3: grazing
+        d /= np.linalg.norm(d)
+        max_t = float(rng.uniform(0.001, 0.12))
+        b1, t1 = scan(o, d, max_t); b2, t2, vis = walk(o, d, max_t)
+        assert (b1, t1) == (b2, t2), (trial, kind, b1, t1, b2, t2)
+        hits += b1 >= 0; contacts += (b1 >= 0 and t1 == 0.0); visited_total += vis
+    assert hits > trials // 4 and contacts > 20
+    assert visited_total < 0.1 * trials * n                                   # and the walk does prune
