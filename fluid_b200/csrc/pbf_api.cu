@@ -103,11 +103,11 @@ void free_arrays(pbf_handle* h) {
 // capacity in particles (sorted entries incl. ghosts and append slots); +1 for the sentinel
 int pbf::alloc_particle_arrays(Solver* hs, size_t n) {
   pbf_handle* h = static_cast<pbf_handle*>(hs);
-  if (n + 1 <= h->cap) return PBF_OK;
-  free_arrays(h);
   // +1: the sentinel particle lives at index n_sorted; +32: the neighbour build reads candidates in
   // unconditional groups of 8 and may run past the last particle (masked off)
   const size_t cap = (n + 1 + 31) / 32 * 32 + 32;
+  if (cap <= h->cap) return PBF_OK;               // the PADDED requirement: a larger n that fits the old rounding must not lose the +32
+  free_arrays(h);
   for (int b = 0; b < 2; b++) { CK(h, dmalloc(&h->pos[b], cap)); CK(h, dmalloc(&h->vel[b], cap)); CK(h, dmalloc(&h->orig[b], cap)); }
   CK(h, dmalloc(&h->xs_tmp, cap)); CK(h, dmalloc(&h->xs_a, cap)); CK(h, dmalloc(&h->xs_b, cap));
   CK(h, dmalloc(&h->vtmp, cap)); CK(h, dmalloc(&h->omega, cap)); CK(h, dmalloc(&h->rho, cap)); CK(h, dmalloc(&h->xv, 2 * cap));
@@ -269,7 +269,7 @@ void pbf_destroy(pbf_handle* h) {
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   delete static_cast<HandleExtra*>(h->host_extra);
-  cudaFree(h->tri_dev); cudaFree(h->bvh_dev); cudaFree(h->tri_id_dev);
+  cudaFree(h->tri_dev); cudaFree(h->bvh_dev); cudaFree(h->tri_id_dev); cudaFree(h->alert_buf);
   delete h;
 }
 
@@ -338,31 +338,37 @@ int pbf::io_download(Solver* hs, double* pos_xyz, double* vel_xyz, double* densi
 
 extern "C" {
 
-int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz) {
-  if (!h || (n && (!pos_xyz || !vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload: null argument");
-  if (n > 0xFFFFFFF0ull) return fail(h, PBF_ERR_INVALID, "pbf_upload: more than 2^32 particles");
+// What every (re-)upload of a single-GPU handle resets before new particles arrive: capacity, copies still in flight on
+// the read-back stream, read-back targets sized for another n, captured graphs, and every "derived from the old
+// positions" marker (neighbour lists, the re-binned cell grid of pbf_density_at / pbf_extract_surface).
+static int begin_upload(pbf_handle* h, size_t n, const char* who) {
+  if (n > 0xFFFFFFF0ull) return fail(h, PBF_ERR_INVALID, "upload: more than 2^32 particles");
   if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
+  (void)who;
   CK(h, cudaSetDevice(h->device));
-  int rc = ensure_capacity(h, n);
-  if (rc != PBF_OK) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
   if (h->copy_stream) CK(h, cudaStreamSynchronize(h->copy_stream));
   h->rb_pending = false;
+  int rc = ensure_capacity(h, n);
+  if (rc != PBF_OK) return rc;
   if (n != h->n) h->rb_pos = h->rb_vel = h->rb_rho = nullptr;          // read-back targets were sized for the old n
   h->graph_invalidate();                              // grids and buffers are baked into the captured step
   h->n = n; h->cur = 0; h->have_neighbors = false; h->rebinned_at = -1;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
+  return PBF_OK;
+}
+
+int pbf_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz) {
+  if (!h || (n && (!pos_xyz || !vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload: null argument");
+  int rc = begin_upload(h, n, "pbf_upload");
+  if (rc != PBF_OK) return rc;
   return io_upload(h, n, pos_xyz, vel_xyz);
 }
 
 int pbf_upload_device(pbf_handle* h, size_t n, const float* d_pos_xyz, const float* d_vel_xyz) {
   if (!h || (n && (!d_pos_xyz || !d_vel_xyz))) return fail(h, PBF_ERR_INVALID, "pbf_upload_device: null argument");
-  CK(h, cudaSetDevice(h->device));
-  int rc = ensure_capacity(h, n);
+  int rc = begin_upload(h, n, "pbf_upload_device");
   if (rc != PBF_OK) return rc;
-  if (h->slab) return fail(h, PBF_ERR_INVALID, "slab mode: use pbf_slab_upload");
-  h->graph_invalidate();
-  h->n = n; h->cur = 0; h->have_neighbors = false;
-  h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
   enqueue_import(h, d_pos_xyz, d_vel_xyz);
   CK(h, cudaStreamSynchronize(h->stream));
   CK(h, cudaGetLastError());
@@ -710,6 +716,52 @@ int pbf_host_unregister(pbf_handle* h, void* ptr) {
   for (size_t k = 0; k < x->regs.size(); k++)
     if (x->regs[k].p == (char*)ptr) { cudaHostUnregister(ptr); x->regs.erase(x->regs.begin() + k); return PBF_OK; }
   return fail(h, PBF_ERR_INVALID, "pbf_host_unregister: pointer was not registered");
+}
+
+// Neighbour-count alert of the reference (particles.cpp:32,165-173): see include/pbf_b200.h
+int pbf_set_neighbor_alert(pbf_handle* h, int threshold, size_t max_records) {
+  if (!h || threshold < 0) return fail(h, PBF_ERR_INVALID, "pbf_set_neighbor_alert: bad argument");
+  if (h->slab) return fail(h, PBF_ERR_INVALID, "pbf_set_neighbor_alert is single-GPU only");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->graph_invalidate();                               // the alert kernel is part of the captured step
+  if (h->alert_buf) { cudaFree(h->alert_buf); h->alert_buf = nullptr; }
+  h->alert_thr = 0; h->alert_cap = 0;
+  if (threshold == 0 || max_records == 0) return PBF_OK;
+  CK(h, dmalloc(&h->alert_buf, 2 * max_records + 4096 / 4));        // records + the 4096-bucket id histogram
+  unsigned int zero[3] = {0, 0, 0};
+  CK(h, cudaMemcpy(&h->sc->alert_count, zero, sizeof(zero), cudaMemcpyHostToDevice));
+  h->alert_thr = (uint32_t)threshold; h->alert_cap = max_records;
+  return PBF_OK;
+}
+
+int pbf_get_neighbor_alerts(pbf_handle* h, size_t cap, uint32_t* ids, uint32_t* counts, double* xpred_xyz, double* vel_xyz, size_t* n_written,
+                            size_t* n_total) {
+  if (!h || !n_total || !n_written) return PBF_ERR_INVALID;
+  *n_total = 0; *n_written = 0;
+  if (h->alert_thr == 0 || !h->alert_buf) return PBF_OK;
+  int rc = pbf_sync(h);
+  if (rc != PBF_OK) return rc;
+  Scalars s;
+  CK(h, cudaMemcpy(&s, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+  *n_total = s.alert_count;
+  const size_t m = std::min<size_t>(s.alert_kept, h->alert_cap);
+  if (m == 0 || cap == 0) return PBF_OK;
+  *n_written = std::min(m, cap);
+  std::vector<float4> rec(2 * m);
+  CK(h, cudaMemcpy(rec.data(), h->alert_buf, 2 * m * sizeof(float4), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> order(m);
+  for (size_t k = 0; k < m; k++) order[k] = (uint32_t)k;
+  auto id_of = [&](uint32_t k) { uint32_t v; std::memcpy(&v, &rec[2 * (size_t)k].w, 4); return v; };
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return id_of(a) < id_of(b); });   // the reference warns in index order
+  for (size_t q = 0; q < std::min(m, cap); q++) {
+    const float4 x = rec[2 * (size_t)order[q]], v = rec[2 * (size_t)order[q] + 1];
+    if (ids) ids[q] = id_of(order[q]);
+    if (counts) std::memcpy(&counts[q], &v.w, 4);
+    if (xpred_xyz) { xpred_xyz[3 * q] = x.x; xpred_xyz[3 * q + 1] = x.y; xpred_xyz[3 * q + 2] = x.z; }
+    if (vel_xyz) { vel_xyz[3 * q] = v.x; vel_xyz[3 * q + 1] = v.y; vel_xyz[3 * q + 2] = v.z; }
+  }
+  return PBF_OK;
 }
 
 // ---- parity / debug ---------------------------------------------------------------------------

@@ -20,6 +20,9 @@ struct Scalars {
   double rho_first, rho_final;     // sum of densities: first lambda pass / finalize pass
   unsigned int counters[8];        // slab packing cursors: emigrants L/R, ghosts L/R
   unsigned int bounds[8];          // slab: cell_start at the column boundaries after the sort
+  unsigned int alert_count;        // particles below the neighbour-count alert threshold in the last step
+  unsigned int alert_kept;         // ... of which this many have a record (ids below alert_bound)
+  unsigned int alert_bound, pad2;
 };
 
 enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
@@ -67,14 +70,17 @@ struct Solver {
   uint32_t* tri_id_dev = nullptr;    // leaf order -> original triangle index, dp.tri_id
   size_t bvh_nodes = 0; int bvh_depth = 0;
   int capture_xpred = 0;
+  // neighbour-count alert (Particle::initializeWithNewNeighbors, particles.cpp:165-173): records of the last step
+  uint32_t alert_thr = 0; size_t alert_cap = 0;
+  float4* alert_buf = nullptr;       // 2 float4 per record: (x*, id bits), (v, count bits); then the id histogram (k_alert_hist)
   bool have_neighbors = false;
-  long long rebinned_at = -1;
+  long long rebinned_at = -1;     // steps_done when the arrays were last re-binned by committed position
   // streaming read-back (pbf_set_readback): results leave for page-locked host buffers as soon as each is final
   double *rb_pos = nullptr, *rb_vel = nullptr, *rb_rho = nullptr;
   double* rb_stage = nullptr;        // device staging, 7 doubles per particle (owned by pbf_api.cu)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_rb[4] = {nullptr, nullptr, nullptr, nullptr};   // positions final, density final, velocity final, copies done
-  bool rb_pending = false;        // steps_done when the arrays were last re-binned by committed position
+  bool rb_pending = false;        // read-back copies of the last step may still be in flight on copy_stream (ev_rb[3])
 
   // Launch-bound scenes (the reference's own p.xml / spheres_p.xml: 720 / 2106 particles, 36 launches of a few
   // microseconds each): the step's launch sequence is captured once per buffer parity (`cur` flips every

@@ -400,6 +400,49 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   for (; s & 3u; s++) out[(size_t)(s >> 2) * 128u + (s & 3u)] = sentinel;   // sentinel padding
 }
 
+// Particle::initializeWithNewNeighbors (particles.cpp:165-173) warns about every particle with fewer than
+// NUM_NEIGHBOR_ALERT_THRESHOLD neighbours, printing its predicted position and velocity, in index order.  The counts
+// are already on the device.  Three small kernels keep the output a pure function of the state although the
+// compaction uses atomics: (1) histogram of the flagged particles over ALERT_BUCKETS ranges of the original id,
+// (2) the largest bucket boundary B with at most `cap` flagged ids below it, (3) records of the flagged particles with
+// id < B (the host sorts them by id): "the first m <= cap warnings in index order", plus the total.
+static constexpr uint32_t ALERT_BUCKETS = 4096;
+__global__ void __launch_bounds__(TPB)
+k_alert_hist(uint32_t n, uint32_t thr, uint32_t shift, const uint32_t* __restrict__ nbr_cnt, const uint32_t* __restrict__ orig,
+             uint32_t* __restrict__ hist) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i < n && nbr_cnt[i] < thr) atomicAdd(&hist[min(orig[i] >> shift, ALERT_BUCKETS - 1u)], 1u);
+}
+__global__ void k_alert_bound(uint32_t cap, uint32_t shift, const uint32_t* __restrict__ hist, Scalars* __restrict__ sc) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t total = 0, kept = 0, bound = 0;
+  bool open_ = true;
+  for (uint32_t b = 0; b < ALERT_BUCKETS; b++) {
+    const uint32_t c = hist[b];
+    if (open_ && kept + c <= cap) { kept += c; bound = b + 1; } else open_ = false;
+    total += c;
+  }
+  sc->alert_count = total;
+  sc->alert_kept = 0;
+  sc->alert_bound = bound >= ALERT_BUCKETS ? 0xFFFFFFFFu : bound << shift;     // ids below this are reported
+}
+__global__ void __launch_bounds__(TPB)
+k_neighbor_alert(uint32_t n, uint32_t thr, const uint32_t* __restrict__ nbr_cnt, const uint32_t* __restrict__ orig,
+                 const float4* __restrict__ xs, const float4* __restrict__ vel, float4* __restrict__ out, uint32_t cap,
+                 Scalars* __restrict__ sc) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = nbr_cnt[i];
+  if (c >= thr) return;
+  const uint32_t id = orig[i];
+  if (id >= sc->alert_bound) return;
+  const uint32_t slot = atomicAdd(&sc->alert_kept, 1u);
+  if (slot >= cap) return;                                  // cannot happen: the bound admits at most cap
+  const float4 x = xs[i], v = vel[i];
+  out[2 * (size_t)slot] = make_float4(x.x, x.y, x.z, __uint_as_float(id));
+  out[2 * (size_t)slot + 1] = make_float4(v.x, v.y, v.z, __uint_as_float(c));
+}
+
 // the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
 __global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega, float4* xv) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -857,6 +900,9 @@ static inline unsigned blocks_for(size_t n, int per_block = TPB) { return (unsig
 // current buffers (or just re-bin committed positions when apply_forces == 0) and hash it.
 void enqueue_predict_hash(Solver* h, int apply_forces) {
   const int cur = h->cur;
+  // every path that re-sorts (step, estimate_densities, re-binning for the density field / surfacer) starts here: the
+  // copy stream may still be exporting xs_a / rho / vel through the old orig[] permutation (pbf_step is asynchronous)
+  if (h->rb_pending) { cudaStreamWaitEvent(h->stream, h->ev_rb[3], 0); h->rb_pending = false; }
   cudaMemsetAsync(h->cell_count, 0, sizeof(uint32_t) * h->ncell, h->stream);
   cudaMemsetAsync(h->cell_of, 0xFF, sizeof(uint32_t) * h->n_in_cap(), h->stream);
   cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
@@ -998,13 +1044,24 @@ void enqueue_readback_all(Solver* h) {
 void enqueue_step(Solver* h, bool readback) {
   const uint32_t n = (uint32_t)h->n;
   if (n == 0) return;
-  if (h->rb_pending) { cudaStreamWaitEvent(h->stream, h->ev_rb[3], 0); h->rb_pending = false; }   // copies still read xs_a / rho / vel
   cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);   // rho_first, rho_final
   h->r_i0 = 0; h->r_cnt = n; h->n_sorted = n;
   enqueue_predict_hash(h, 1);
   enqueue_sort(h, n);
   enqueue_build(h, 0);
   if (h->capture_xpred) cudaMemcpyAsync(h->xpred, h->xs_a, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream);
+  if (h->alert_thr > 0 && h->alert_buf) {
+    uint32_t* hist = reinterpret_cast<uint32_t*>(h->alert_buf + 2 * h->alert_cap);
+    uint32_t shift = 0;
+    while (((uint64_t)ALERT_BUCKETS << shift) < (uint64_t)n) shift++;
+    cudaMemsetAsync(hist, 0, ALERT_BUCKETS * sizeof(uint32_t), h->stream);
+    LAUNCH(h, K_IO, k_alert_hist, blocks_for(n), n, h->alert_thr, shift, h->nbr_cnt, h->orig[h->cur], hist);
+    h->prof_begin(K_IO);
+    k_alert_bound<<<1, 32, 0, h->stream>>>((uint32_t)h->alert_cap, shift, hist, h->sc);
+    h->prof_end(K_IO); h->launches++;
+    LAUNCH(h, K_IO, k_neighbor_alert, blocks_for(n), n, h->alert_thr, h->nbr_cnt, h->orig[h->cur], h->xs_a, h->vel[h->cur], h->alert_buf,
+           (uint32_t)h->alert_cap, h->sc);
+  }
   for (int it = 0; it < h->dp.iterations; it++) { enqueue_lambda(h, it == 0, PART_ALL); enqueue_delta(h, PART_ALL); }
   readback = readback && h->copy_stream && (h->rb_pos || h->rb_vel || h->rb_rho);
   if (readback) readback_piece(h, h->ev_rb[0], 0);          // positions are final once the iterations end

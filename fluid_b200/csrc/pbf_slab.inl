@@ -191,7 +191,7 @@ int pbf_slab_configure(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int r
 
 int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz, const uint32_t* ids) {
   if (!h || !h->slab || (n && (!pos_xyz || !vel_xyz || !ids))) return sfail(h, PBF_ERR_INVALID, "pbf_slab_upload: bad argument / not configured");
-  if (n + 4 * h->halo_cap + 1 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "pbf_slab_upload: more particles than particle_cap");
+  if (n + 4 * h->halo_cap + 33 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "pbf_slab_upload: more particles than particle_cap");
   SCK(h, cudaSetDevice(h->device));
   h->n = n; h->cur = 0; h->have_neighbors = false;
   h->r_i0 = 0; h->r_cnt = (uint32_t)n; h->n_sorted = (uint32_t)n;
@@ -206,7 +206,7 @@ int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double
 int pbf_slab_phase_predict(pbf_handle* h) {
   if (!h || !h->slab) return PBF_ERR_INVALID;
   SCK(h, cudaSetDevice(h->device));
-  if ((size_t)h->n_sorted + 4 * h->halo_cap + 1 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded");
+  if ((size_t)h->n_sorted + 4 * h->halo_cap + 33 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded");
   cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);
   enqueue_predict_hash(h, 1);
   h->prof_begin(K_SLAB);
@@ -264,7 +264,7 @@ int pbf_slab_phase_sort(pbf_handle* h, uint32_t bounds_out[5]) {
   h->n_sorted = s.bounds[4];
   h->r_i0 = s.bounds[0]; h->r_cnt = s.bounds[3] - s.bounds[0];
   h->n = h->r_cnt;
-  if ((size_t)h->n_sorted + 1 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded");
+  if ((size_t)h->n_sorted + 33 > h->cap) return sfail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded");   // +1 sentinel, +32 unconditional candidate groups
   enqueue_build(h, 0);
   h->have_neighbors = true;
   if (bounds_out) for (int k = 0; k < 5; k++) bounds_out[k] = h->bounds[k];

@@ -1,7 +1,9 @@
 // particles_b200.cpp — see particles_b200.h.  Host C++ only; the GPU is reached through the C ABI.
 #include "particles_b200.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,23 +13,41 @@
 
 namespace pbfhost {
 
-Particles::Particles(double rho0, const PbfParams* params, int device)
-    : simulate_time(0.0), rest_density(rho0), device_(device) {
+Particles::Particles(double rho0, const PbfParams* params, int device, bool quiet_ctor)
+    : simulate_time(0.0), rest_density(rho0), quiet(quiet_ctor), device_(device) {
   if (params) params_ = *params; else pbf_default_params(&params_);
   params_.rest_density = rho0;
   if (!quiet) { fprintf(stdout, "%s", paramsString().c_str()); fflush(stdout); }   // particles.h:114-116
 }
 
 Particles::~Particles() {
-  for (Particle* p : ps) delete p;
   if (handle_) pbf_destroy(handle_);
 }
 
 const char* Particles::lastError() const { return handle_ ? pbf_last_error(handle_) : "no device handle"; }
 
+// (Re)create the views after the mirror arrays moved: all four containers grow together, so this runs O(log n) times.
+void Particles::rebind() {
+  const size_t n = rho_.size();
+  const size_t cap = std::max<size_t>(1024, 2 * n);
+  pos_.reserve(3 * cap); vel_.reserve(3 * cap); rho_.reserve(cap);
+  storage_.clear(); storage_.reserve(cap);
+  ps.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    storage_.emplace_back(reinterpret_cast<Vector3D*>(&pos_[3 * i]), reinterpret_cast<Vector3D*>(&vel_[3 * i]), &rho_[i], rest_density);
+    ps[i] = &storage_[i];
+  }
+}
+
 void Particles::addParticle(Vector3D pos, Vector3D v) {
   if (uploaded_) { std::cerr << "[pbf_b200] addParticle after the first step is not supported" << std::endl; std::exit(EXIT_FAILURE); }
-  ps.push_back(new Particle(pos, v, rest_density));
+  const bool grow = rho_.size() == rho_.capacity() || storage_.size() == storage_.capacity();
+  const double p3[3] = {pos.x, pos.y, pos.z}, v3[3] = {v.x, v.y, v.z};
+  pos_.insert(pos_.end(), p3, p3 + 3); vel_.insert(vel_.end(), v3, v3 + 3); rho_.push_back(0.0);
+  if (grow) { rebind(); return; }
+  const size_t i = rho_.size() - 1;
+  storage_.emplace_back(reinterpret_cast<Vector3D*>(&pos_[3 * i]), reinterpret_cast<Vector3D*>(&vel_[3 * i]), &rho_[i], rest_density);
+  ps.push_back(&storage_.back());
 }
 
 void Particles::ensureUploaded() {
@@ -38,12 +58,8 @@ void Particles::ensureUploaded() {
     std::exit(EXIT_FAILURE);
   }
   const size_t n = ps.size();
-  pos_.resize(3 * n); vel_.resize(3 * n); rho_.assign(n, 0.0);
-  for (size_t i = 0; i < n; i++) {
-    pos_[3*i] = ps[i]->position.x; pos_[3*i+1] = ps[i]->position.y; pos_[3*i+2] = ps[i]->position.z;
-    vel_[3*i] = ps[i]->velocity.x; vel_[3*i+1] = ps[i]->velocity.y; vel_[3*i+2] = ps[i]->velocity.z;
-  }
-  // the mirror arrays live as long as the handle: page-lock them once so every step's read-back is a direct DMA
+  // the mirror arrays live as long as the handle (addParticle is refused from here on): page-lock them once so every
+  // step's read-back is a direct DMA
   if (n) { pbf_host_register(handle_, pos_.data(), 3 * n * sizeof(double)); pbf_host_register(handle_, vel_.data(), 3 * n * sizeof(double));
            pbf_host_register(handle_, rho_.data(), n * sizeof(double)); }
   if (!spheres_.empty() && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
@@ -55,20 +71,31 @@ void Particles::ensureUploaded() {
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   if (n) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data());   // every step streams its result into the mirror
+  if (n && neighbor_alert_threshold > 0) pbf_set_neighbor_alert(handle_, neighbor_alert_threshold, std::max<size_t>(neighbor_alert_max_lines, 1));
   uploaded_ = true;
 }
 
+// `ps` are views into pos_ / vel_ / rho_, so completing the transfer IS the refresh
 void Particles::refreshMirror(bool already_streamed) {
-  const size_t n = ps.size();
   // after a step the streaming read-back has the data on its way: pbf_sync completes it
   int rc = already_streamed ? pbf_sync(handle_) : pbf_download(handle_, pos_.data(), vel_.data(), rho_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] step failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
-  for (size_t i = 0; i < n; i++) {
-    Particle* p = ps[i];
-    p->position = Vector3D(pos_[3*i], pos_[3*i+1], pos_[3*i+2]);
-    p->velocity = Vector3D(vel_[3*i], vel_[3*i+1], vel_[3*i+2]);
-    p->density = rho_[i];
-  }
+}
+
+// particles.cpp:165-173: `cerr << *this << " only has " << neighbors.size() << " neighbors."` with
+// operator<<(Particle) = "P(p" << new_position << ",v" << velocity << ')' (particles.cpp:153-156)
+void Particles::reportNeighborAlerts() {
+  neighbor_alerts_last_step = 0;
+  if (quiet || neighbor_alert_threshold <= 0 || !handle_) return;
+  const size_t cap = std::max<size_t>(neighbor_alert_max_lines, 1);
+  std::vector<uint32_t> ids(cap), cnt(cap); std::vector<double> xp(3 * cap), vp(3 * cap);
+  size_t total = 0, shown = 0;
+  if (pbf_get_neighbor_alerts(handle_, cap, ids.data(), cnt.data(), xp.data(), vp.data(), &shown, &total) != PBF_OK) return;
+  neighbor_alerts_last_step = total;
+  for (size_t k = 0; k < shown; k++)
+    std::cerr << "P(p(" << xp[3*k] << "," << xp[3*k+1] << "," << xp[3*k+2] << "),v(" << vp[3*k] << "," << vp[3*k+1] << "," << vp[3*k+2] << "))"
+              << " only has " << cnt[k] << " neighbors." << std::endl;
+  if (total > shown) std::cerr << "[pbf_b200] ... and " << (total - shown) << " more particles with fewer than " << neighbor_alert_threshold << " neighbors." << std::endl;
 }
 
 void Particles::estimateDensities() {
@@ -102,6 +129,7 @@ void Particles::timeStep(double delta_t) {
   if (!quiet) std::cerr << " => " << simulate_time << std::endl;
   if (pbf_step(handle_, 1) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   refreshMirror(/*already_streamed=*/ps.size() > 0);
+  reportNeighborAlerts();                                        // particles.cpp:268-270 (initializeWithNewNeighbors)
   double ms = 0;
   pbf_stats(handle_, &avg_rho_first_iter, &avg_rho_final, &ms);
   if (!quiet) std::cout << "avg rho: " << avg_rho_first_iter << " => " << avg_rho_final << std::endl;   // particles.cpp:267,279,295
@@ -139,7 +167,7 @@ double Particles::estimateDensityAt(Vector3D pos) const {
   double H9 = 1; for (int i = 0; i < 9; i++) H9 *= H;
   double density = 0.0;
   for (const Particle* p : ps) {
-    const double dx = p->position.x - pos.x, dy = p->position.y - pos.y, dz = p->position.z - pos.z;
+    const double dx = p->position->x - pos.x, dy = p->position->y - pos.y, dz = p->position->z - pos.z;
     const double r2 = dx * dx + dy * dy + dz * dz;
     if (r2 >= H2) continue;
     const double t = H2 - r2;
@@ -160,44 +188,48 @@ std::vector<double> Particles::estimateDensitiesAt(const std::vector<Vector3D>& 
 bool Particles::saveCheckpoint(const char* filename, std::string* error) const {
   FILE* f = fopen(filename, "wb");
   if (!f) { if (error) *error = std::string("cannot open ") + filename; return false; }
-  const int64_t n = (int64_t)ps.size(), steps = steps_taken, psz = (int64_t)sizeof(PbfParams), ns = (int64_t)(spheres_.size() / 4);
-  std::vector<double> buf(7 * (size_t)n);
-  for (int64_t i = 0; i < n; i++) {                // from the host mirror: exactly the fp32 device state, widened
-    const Particle* p = ps[i];
-    buf[3*i] = p->position.x; buf[3*i+1] = p->position.y; buf[3*i+2] = p->position.z;
-    buf[3*n + 3*i] = p->velocity.x; buf[3*n + 3*i+1] = p->velocity.y; buf[3*n + 3*i+2] = p->velocity.z;
-    buf[6*n + i] = p->density;
-  }
-  bool ok = fwrite("PBFCKPT1", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&steps, 8, 1, f) == 1 &&
+  const int64_t n = (int64_t)ps.size(), steps = steps_taken, psz = (int64_t)sizeof(PbfParams), ns = (int64_t)(spheres_.size() / 4),
+                nt = (int64_t)(tris_.size() / 18);
+  // the host mirror is exactly the fp32 device state, widened
+  bool ok = fwrite("PBFCKPT2", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&steps, 8, 1, f) == 1 &&
             fwrite(&simulate_time, 8, 1, f) == 1 && fwrite(&rest_density, 8, 1, f) == 1 && fwrite(&psz, 8, 1, f) == 1 &&
             fwrite(&params_, sizeof(PbfParams), 1, f) == 1 && fwrite(&ns, 8, 1, f) == 1 &&
             (ns == 0 || fwrite(spheres_.data(), 8, spheres_.size(), f) == spheres_.size()) &&
-            (n == 0 || fwrite(buf.data(), 8, buf.size(), f) == buf.size());
+            fwrite(&nt, 8, 1, f) == 1 && (nt == 0 || fwrite(tris_.data(), 8, tris_.size(), f) == tris_.size()) &&
+            (n == 0 || (fwrite(pos_.data(), 8, 3 * (size_t)n, f) == 3 * (size_t)n && fwrite(vel_.data(), 8, 3 * (size_t)n, f) == 3 * (size_t)n &&
+                        fwrite(rho_.data(), 8, (size_t)n, f) == (size_t)n));
   ok = (fclose(f) == 0) && ok;
   if (!ok && error) *error = std::string("short write to ") + filename;
   return ok;
 }
 
-Particles* Particles::loadCheckpoint(const char* filename, std::string* error, int device) {
+Particles* Particles::loadCheckpoint(const char* filename, std::string* error, int device, bool quiet_ctor) {
   auto fail = [&](const std::string& m) -> Particles* { if (error) *error = m; return nullptr; };
   FILE* f = fopen(filename, "rb");
   if (!f) return fail(std::string("cannot open ") + filename);
-  char magic[8]; int64_t n = 0, steps = 0, psz = 0, ns = 0; double t = 0, rho0 = 0; PbfParams prm;
-  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "PBFCKPT1", 8) == 0 && fread(&n, 8, 1, f) == 1 && fread(&steps, 8, 1, f) == 1 &&
-            fread(&t, 8, 1, f) == 1 && fread(&rho0, 8, 1, f) == 1 && fread(&psz, 8, 1, f) == 1 && psz == (int64_t)sizeof(PbfParams) &&
-            fread(&prm, sizeof(PbfParams), 1, f) == 1 && fread(&ns, 8, 1, f) == 1 && n >= 0 && ns >= 0 && ns <= PBF_MAX_SPHERES;
-  if (!ok) { fclose(f); return fail("not a PBFCKPT1 checkpoint (or written with another PbfParams layout)"); }
-  std::vector<double> sph(4 * (size_t)ns), buf(7 * (size_t)n);
-  ok = (ns == 0 || fread(sph.data(), 8, sph.size(), f) == sph.size()) && (n == 0 || fread(buf.data(), 8, buf.size(), f) == buf.size());
+  char magic[8]; int64_t n = 0, steps = 0, psz = 0, ns = 0, nt = 0; double t = 0, rho0 = 0; PbfParams prm;
+  bool ok = fread(magic, 1, 8, f) == 8 && (memcmp(magic, "PBFCKPT2", 8) == 0 || memcmp(magic, "PBFCKPT1", 8) == 0);
+  const bool v2 = ok && magic[7] == '2';
+  ok = ok && fread(&n, 8, 1, f) == 1 && fread(&steps, 8, 1, f) == 1 &&
+       fread(&t, 8, 1, f) == 1 && fread(&rho0, 8, 1, f) == 1 && fread(&psz, 8, 1, f) == 1 && psz == (int64_t)sizeof(PbfParams) &&
+       fread(&prm, sizeof(PbfParams), 1, f) == 1 && fread(&ns, 8, 1, f) == 1 && n >= 0 && ns >= 0 && ns <= PBF_MAX_SPHERES;
+  if (!ok) { fclose(f); return fail("not a PBFCKPT checkpoint (or written with another PbfParams layout)"); }
+  std::vector<double> sph(4 * (size_t)ns), tri, buf(7 * (size_t)n);
+  ok = ns == 0 || fread(sph.data(), 8, sph.size(), f) == sph.size();
+  if (ok && v2) {
+    ok = fread(&nt, 8, 1, f) == 1 && nt >= 0 && (uint64_t)nt <= PBF_MAX_TRIANGLES;
+    if (ok) { tri.resize(18 * (size_t)nt); ok = nt == 0 || fread(tri.data(), 8, tri.size(), f) == tri.size(); }
+  }
+  ok = ok && (n == 0 || fread(buf.data(), 8, buf.size(), f) == buf.size());
   fclose(f);
   if (!ok) return fail("truncated checkpoint");
-  Particles* ps = new Particles(rho0, &prm, device);
-  for (int64_t i = 0; i < n; i++) {
+  Particles* ps = new Particles(rho0, &prm, device, quiet_ctor);
+  for (int64_t i = 0; i < n; i++)
     ps->addParticle(Vector3D(buf[3*i], buf[3*i+1], buf[3*i+2]), Vector3D(buf[3*n + 3*i], buf[3*n + 3*i+1], buf[3*n + 3*i+2]));
-    ps->ps.back()->density = buf[6*n + i];
-  }
+  for (int64_t i = 0; i < n; i++) ps->rho_[i] = buf[6*n + i];
   ps->simulate_time = t; ps->steps_taken = steps;
   if (ns) ps->setObstacleSpheres(sph);
+  if (nt) ps->setObstacleTriangles(tri);
   return ps;
 }
 
@@ -282,10 +314,10 @@ bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::ve
   return true;
 }
 
-Particles* load_particles_xml(const char* filename, std::string* error, const PbfParams* params, int device) {
+Particles* load_particles_xml(const char* filename, std::string* error, const PbfParams* params, int device, bool quiet) {
   std::vector<double> pos, vel; double rho0 = 1000.0;
   if (!parse_particles_xml(filename, pos, vel, rho0, error)) return nullptr;
-  Particles* particles = new Particles(rho0, params, device);
+  Particles* particles = new Particles(rho0, params, device, quiet);
   const size_t n = pos.size() / 3;
   for (size_t i = 0; i < n; i++)
     particles->addParticle(Vector3D(pos[3*i], pos[3*i+1], pos[3*i+2]), Vector3D(vel[3*i], vel[3*i+1], vel[3*i+2]));

@@ -27,19 +27,21 @@ struct Color { float r, g, b, a; };
 
 class Particle {   // particles.h:19-91: the read-only part the visualiser / surfacer use
  public:
-  Vector3D velocity;
-  Particle(const Vector3D& p, const Vector3D& v, double rho0) : velocity(v), position(p), density(0), rest_density(rho0) {}
-  double getLatestDensityEstimate() const { return density; }
-  Vector3D getPosition() const { return position; }
+  // A VIEW: position / velocity / density live in the owner's contiguous AoS arrays (the buffers the C ABI reads and
+  // the streaming read-back writes), so refreshing the mirror after a step costs nothing per particle.
+  Vector3D& velocity;                                        // particles.h:21 (public member of the reference)
+  Particle(Vector3D* p, Vector3D* v, const double* rho, double rho0) : velocity(*v), position(p), density(rho), rest_density(rho0) {}
+  double getLatestDensityEstimate() const { return *density; }
+  Vector3D getPosition() const { return *position; }
   Color getDensityBasedColor() const {   // particles.h:48-52
-    double ratio = (density - 0.8 * rest_density) / (0.4 * rest_density);
+    double ratio = (*density - 0.8 * rest_density) / (0.4 * rest_density);
     double c = ratio < 0.0 ? 0.0 : (ratio > 1.0 ? 1.0 : ratio);
     return Color{1.0f, (float)(1.0 - c), (float)(1.0 - c), 1.0f};
   }
  private:
   friend struct Particles;
-  Vector3D position;
-  double density;
+  Vector3D* position;
+  const double* density;
   double rest_density;
 };
 
@@ -55,8 +57,17 @@ struct Particles {
   // lattice of the surfacer: the reference hard-codes the Cornell box (particles.cpp:326-350)
   Vector3D surface_min = Vector3D(-1, 0, -1), surface_max = Vector3D(1, 1.5, 1);
   bool quiet = false;                  // the reference prints two lines per step (Q16); keep, but allow silence
+  // Particle::initializeWithNewNeighbors (particles.cpp:165-173) warns on cerr about every particle with fewer than
+  // NUM_NEIGHBOR_ALERT_THRESHOLD (18, particles.cpp:32) neighbours.  Kept (unless quiet): the first
+  // neighbor_alert_max_lines lines are printed in the reference's wording and index order, then one summary line
+  // (the reference would print one line per particle: 100 per step on p.xml, millions on a large free surface).
+  int neighbor_alert_threshold = 18;
+  size_t neighbor_alert_max_lines = 128;
+  size_t neighbor_alerts_last_step = 0;   // how many particles were below the threshold in the last timeStep
 
-  explicit Particles(double rest_density = 1000.0, const PbfParams* params = nullptr, int device = 0);
+  // quiet_ctor: the reference prints the parameter banner from the constructor (particles.h:114-116), i.e. before a
+  // caller could set `quiet`
+  explicit Particles(double rest_density = 1000.0, const PbfParams* params = nullptr, int device = 0, bool quiet_ctor = false);
   ~Particles();
   Particles(const Particles&) = delete;
   Particles& operator=(const Particles&) = delete;
@@ -78,13 +89,14 @@ struct Particles {
   double estimateDensityAt(Vector3D pos) const;  // particles.cpp:446-453 (host loop over the mirror, one point)
   // the same field for many points at once on the GPU (pbf_density_at): what a surfacer should call
   std::vector<double> estimateDensitiesAt(const std::vector<Vector3D>& points);
-  // Restart file: magic "PBFCKPT1", int64 n, int64 steps, double simulate_time, double rho0,
-  // int64 sizeof(PbfParams) + the struct, int64 number of obstacle spheres + rows, then pos[3n], vel[3n],
-  // density[n] as little-endian doubles in original particle order.  The device state is fp32 and its layout is
+  // Restart file: magic "PBFCKPT2", int64 n, int64 steps, double simulate_time, double rho0,
+  // int64 sizeof(PbfParams) + the struct, int64 number of obstacle spheres + rows, int64 number of obstacle
+  // triangles + 18 doubles each, then pos[3n], vel[3n], density[n] as little-endian doubles in original particle
+  // order ("PBFCKPT1" files, which had no triangle block, still load).  The device state is fp32 and its layout is
   // a pure function of (positions, velocities, ids), so a run continued from a checkpoint is bit-identical to
   // the uninterrupted run.
   bool saveCheckpoint(const char* filename, std::string* error = nullptr) const;
-  static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0);   // nullptr on error
+  static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false);   // nullptr on error
   long long steps_taken = 0;
   std::string paramsString() const;              // particles.cpp:420-438
   // the two numbers of the reference's "avg rho: a => b" line for the last step
@@ -95,18 +107,23 @@ struct Particles {
  private:
   void ensureUploaded();
   void refreshMirror(bool already_streamed = false);
+  void rebind();
+  void reportNeighborAlerts();
   PbfParams params_;
   int device_;
   pbf_handle* handle_ = nullptr;
   bool uploaded_ = false;
+  // the mirror: AoS xyz doubles in original particle order (Vector3D-compatible), what pbf_upload reads and the
+  // streaming read-back writes; `ps` holds views into them (storage_ = the view objects, contiguous)
   std::vector<double> pos_, vel_, rho_, spheres_, tris_;
+  std::vector<Particle> storage_;
 };
 
 // Application::load_particles (application.cpp:302-344): <particles><density>rho0</density><ps>
 // <particle><pos>x y z</pos><v>x y z</v></particle>...  Density goes through float like stof (Q17).
 // Streaming reader (no DOM), so multi-million-particle files are fine.  Returns nullptr on error.
-Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0);
-inline Particles* load_checkpoint(const char* filename, std::string* error = nullptr, int device = 0) { return Particles::loadCheckpoint(filename, error, device); }
+Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0, bool quiet = false);
+inline Particles* load_checkpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false) { return Particles::loadCheckpoint(filename, error, device, quiet); }
 // parse only: positions / velocities (AoS doubles) and rho0; false on error
 bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::vector<double>& vel, double& rho0, std::string* error);
 

@@ -43,6 +43,8 @@ int main(int argc, char** argv) {
   }
   if (!pfile && !load_state) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
   std::string err;
+  if (parse_only && !pfile) { printf("[ERROR] --parse-only needs -p <particle_file_path>\n"); return 2; }
+  if (load_state && iterations >= 0) { printf("[ERROR] --iterations cannot be combined with --load-state (the checkpoint carries its parameters)\n"); return 2; }
   if (parse_only) {
     std::vector<double> pos, vel; double rho0 = 0;
     if (!parse_particles_xml(pfile, pos, vel, rho0, &err)) { printf("[ERROR] XML error: %s\n", err.c_str()); return 1; }
@@ -55,7 +57,7 @@ int main(int argc, char** argv) {
   PbfParams prm; pbf_default_params(&prm);
   if (iterations >= 0) prm.iterations = iterations;
   printf("[Fluid Simulation] Loading particle file...");
-  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0) : load_particles_xml(pfile, &err, &prm, 0);
+  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0, quiet) : load_particles_xml(pfile, &err, &prm, 0, quiet);
   if (!ps) { printf("[ERROR] %s: %s\n", load_state ? "checkpoint error" : "XML error", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
   printf("Done!\n");
   ps->quiet = quiet;

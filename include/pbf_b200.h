@@ -116,6 +116,17 @@ int  pbf_estimate_densities(pbf_handle* h);     /* load-time density incl. self 
  * (the two numbers the reference prints), and the device time of the last pbf_step call. */
 int  pbf_stats(pbf_handle* h, double* avg_rho_first_iter, double* avg_rho_final, double* last_call_ms);
 
+/* Neighbour-count alert = the cerr warning of Particle::initializeWithNewNeighbors (particles.cpp:165-173: every
+ * particle with fewer than NUM_NEIGHBOR_ALERT_THRESHOLD = 18 neighbours, particles.cpp:32, is reported with its
+ * predicted position and velocity).  With a threshold > 0 every step compacts those particles on the device (one
+ * small kernel over the counts the neighbour build leaves behind); pbf_get_neighbor_alerts returns the records of the
+ * LAST step sorted by particle id (the reference's order; *n_written of them) and the full count in *n_total.  When more than
+ * max_records particles qualify, the records are those with the smallest ids, cut at a multiple of
+ * 2^ceil(log2(n / 4096)) ids so that at most max_records remain: a deterministic prefix of the reference's output.  Any output pointer may be NULL.  threshold 0 switches it off (the default).  Single GPU. */
+int  pbf_set_neighbor_alert(pbf_handle* h, int threshold, size_t max_records);
+int  pbf_get_neighbor_alerts(pbf_handle* h, size_t cap, uint32_t* ids, uint32_t* counts, double* xpred_xyz, double* vel_xyz,
+                             size_t* n_written, size_t* n_total);
+
 /* SPH density at m arbitrary points from the committed positions = Particles::estimateDensityAt
  * (particles.cpp:446-453), the scalar field the marching-cubes surfacer samples
  * (particles.cpp:350-418).  Host fp64 AoS in, fp64 out; single GPU. */

@@ -8,7 +8,7 @@
 // (SURVEY.md §4), so the pin is the unmodified reference itself, compiled headlessly by
 // oracle/Makefile into oracle/_ref/ref_harness: Oracle<double>(XSPH reference order, triangle
 // walls) reproduces its full state and ordered neighbour lists bit-for-bit
-// (tests/test_oracle_vs_reference.py; committed fixtures in tests/golden/).
+// (tests/test_oracle_golden.py; committed fixtures in tests/golden/).
 //
 // Each function cites the reference lines it restates.  Arithmetic ORDER is part of the
 // contract (SURVEY.md §8c "rules"): Vector3D / scalar multiplies by the reciprocal

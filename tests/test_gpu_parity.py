@@ -152,6 +152,87 @@ def test_whole_step_vs_fp32_and_fp64_oracle(name):
             assert np.percentile(dv, 50) <= 1e-3 and np.percentile(dv, 99) <= 5e-3 / 0.016, f"{name}/{label}: dv p50 {np.percentile(dv, 50):.2e}"
 
 
+@pytest.mark.parametrize("name", ["spheres_p", "two_blocks"])
+def test_whole_step_four_iterations(name):
+    """BASELINE config C2: the sphere-drop scene at 4 solver iterations (the reference's NEWTON_NUM_STEPS is a
+    private macro, particles.cpp:34; the CPU side is the oracle at I = 4).  Same gates as the 12-iteration step."""
+    rho0, states = _states(name)
+    for label, pos, vel in states:
+        g = _gpu(rho0, iterations=4); g.upload(pos, vel); g.step(1)
+        Pg, Vg, Rg = g.download()
+        for prec in (32, 64):
+            if prec == 64 and name in SHIPPED and label == "init":
+                continue   # knife-edge lattice (see the 12-iteration test)
+            o = _oracle(rho0, prec, iterations=4); o.upload(pos, vel); o.step(1)
+            Po, Vo, Ro = o.download()
+            if prec == 32:
+                assert np.array_equal(g.neighbor_digest()[0], o.digest()[0])
+            _gate_whole_step(f"{name}/{label}/I=4/fp{prec}", Pg, Rg, Po, Ro, rho0)
+            dv = np.linalg.norm(Vg - Vo, axis=1)
+            assert np.percentile(dv, 50) <= 1e-3 and np.percentile(dv, 99) <= 5e-3 / 0.016
+
+
+FAR_BOXES = {"C4": (120.0, 30.0, 20.1), "C5": (320.1, 30.0, 20.1)}
+
+
+@pytest.mark.parametrize("cfg", ["C4", "C5"])
+def test_far_end_of_the_bench_boxes_vs_oracle(cfg):
+    """The bench workloads reach x = 120 (C4) and x = 320 (C5), where one fp32 ulp is 7.6e-6 / 3.1e-5 and the
+    conservativeness of the neighbour search rests on nb_run_range's slack and the 2^-8 cell margin.  A 32^3 jittered
+    block pressed against the far x wall of each box, from the lattice and from evolved (disordered) states:
+      * x* and the frozen neighbour sets are BIT-EXACT against the fp32 oracle (digest, counts, full CSR);
+      * the whole step stays inside the fp32 noise of the algorithm at these coordinates: the GPU may differ from the
+        fp32 oracle by no more than the fp32 oracle differs from the fp64 oracle on the same state (measured on the
+        CPU: p50 1e-3 / p99 2e-2 on the violent first step at x = 120, p50 2e-5 / p99 8e-4 two steps later; at these
+        coordinates fp32 and fp64 do not even agree on the neighbour SETS, 1 ulp of x decides knife-edge pairs),
+        with the usual gates (p50 1e-5, p99 5e-3, max 0.1) as the floor of the comparison."""
+    from fluid_b200 import api
+    box_max = FAR_BOXES[cfg]
+    prm = dict(rest_density=700.0, box_min=(0.0, 0.0, 0.0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
+    x0 = float(np.float32(box_max[0])) - 3.25                   # last lattice plane 0.15 from the wall
+    pos, vel = lattice_block(32, 32, 32, origin=(x0, 0.1, 0.1), jitter=0.001, seed=77)
+    assert pos[:, 0].max() > box_max[0] - 0.2
+    states = [("lattice", pos, vel)]
+    ge = api.Solver(api.default_params(**prm)); ge.upload(pos, vel)
+    for steps in (3, 12):                                       # evolved states: after the violent start / spreading along the wall
+        ge.step(steps)
+        P, V, _ = ge.download()
+        states.append((f"evolved{steps}", P, V))
+    for label, p0, v0 in states:
+        g = api.Solver(api.default_params(iterations=0, **prm)); g.capture(True); g.upload(p0, v0); g.step(1)
+        o = Oracle(oracle_params(xsph_mode=XSPH_JACOBI, iterations=0, **prm), 32, COLLIDE_BOX, SEARCH_GRID); o.upload(p0, v0); o.step(1)
+        xg = g.array(ARRAY_XPRED); xo = o.array(ARRAY_XPRED)
+        assert np.array_equal(xg, xo), f"{cfg}/{label}: x* differs (max {np.abs(xg - xo).max():.3e})"
+        dg, cg = g.neighbor_digest(); do, co = o.digest()
+        assert np.array_equal(cg, co), f"{cfg}/{label}: neighbour counts differ for {np.count_nonzero(cg != co)} particles"
+        assert np.array_equal(dg, do), f"{cfg}/{label}: neighbour digests differ"
+        rg, colg = g.neighbors(); ro, colo = o.neighbors()
+        assert np.array_equal(rg, ro) and np.array_equal(colg, colo)
+        assert cg.mean() > 40                                   # a fluid, not a gas: the check is not vacuous
+        # whole step, teacher-forced
+        g = api.Solver(api.default_params(**prm)); g.upload(p0, v0); g.step(1)
+        Pg, Vg, Rg = g.download()
+        outs = {}
+        for prec in (32, 64):
+            o = Oracle(oracle_params(xsph_mode=XSPH_JACOBI, **prm), prec, COLLIDE_BOX, SEARCH_GRID); o.upload(p0, v0); o.step(1)
+            outs[prec] = o.download()
+            if prec == 32:
+                assert np.array_equal(g.neighbor_digest()[0], o.digest()[0])
+        fl = np.linalg.norm(outs[32][0] - outs[64][0], axis=1)
+        f50, f99, fmx = np.percentile(fl, 50), np.percentile(fl, 99), fl.max()
+        frho = np.percentile(np.abs(outs[32][2] - outs[64][2]) / 700.0, 99)
+        for prec, k in ((32, 1.0), (64, 2.0)):
+            Po, Vo, Ro = outs[prec]
+            dx = np.linalg.norm(Pg - Po, axis=1)
+            p50, p99, mx = np.percentile(dx, 50), np.percentile(dx, 99), dx.max()
+            drho = np.percentile(np.abs(Rg - Ro) / 700.0, 99)
+            msg = (f"{cfg}/{label}/fp{prec}: |dx| p50 {p50:.2e} p99 {p99:.2e} max {mx:.2e} drho99 {drho:.2e}; "
+                   f"fp32-vs-fp64 oracle floor p50 {f50:.2e} p99 {f99:.2e} max {fmx:.2e} drho99 {frho:.2e}")
+            assert p50 <= max(1e-5, k * f50) and p99 <= max(5e-3, k * f99) and mx <= max(1e-1, 1.5 * k * fmx), msg
+            assert drho <= max(1e-2, k * frho), msg
+        assert np.isfinite(Pg).all() and (Pg[:, 0] <= float(np.float32(box_max[0]))).all()
+
+
 @pytest.mark.parametrize("name", JITTER)
 def test_whole_step_vs_unmodified_reference(name):
     """Direct comparison with the output of the unmodified reference (fp64, triangle walls,
@@ -215,13 +296,20 @@ def test_rollout_drift_vs_fp64_oracle():
     diag = np.linalg.norm([2.0, 1.49, 2.0])
     g = _gpu(rho0); g.upload(pos, vel)
     o = _oracle(rho0, 64); o.upload(pos, vel)
-    for _ in range(5):
-        g.step(5)
+    for k in range(5):
+        g.step(5); o.step(5)
         P, V, _r = g.download()
         g0 = _gpu(rho0, iterations=0); g0.upload(P, V); g0.step(1)
         o0 = _oracle(rho0, 32, iterations=0); o0.upload(P, V); o0.step(1)
         assert np.array_equal(g0.neighbor_digest()[0], o0.digest()[0]), "neighbour sets of an evolved state differ from the fp32 oracle"
-    o.step(25)
+        if k < 2:
+            # steps 5 and 10: the fall has not hit the floor's rebound yet and the fp32 / fp64 oracles are 0.1 % / 0.6 %
+            # apart in kinetic energy (2.2 % at step 12), so the survey's 5 % gate (Appendix B, protocol 5) holds here
+            Po, Vo, Ro = o.download()
+            keg, keo = 0.5 * (V ** 2).sum(), 0.5 * (Vo ** 2).sum()
+            assert abs(keg - keo) <= (0.02 if k == 0 else 0.05) * keo, (k, keg, keo)
+            assert abs(_r.mean() - Ro.mean()) / rho0 <= 0.005
+            assert np.linalg.norm(P.mean(axis=0) - Po.mean(axis=0)) <= 0.002 * diag
     Pg, Vg, Rg = g.download(); Po, Vo, Ro = o.download()
     keg, keo = 0.5 * (Vg ** 2).sum(), 0.5 * (Vo ** 2).sum()
     assert abs(keg - keo) <= 0.30 * keo, (keg, keo)

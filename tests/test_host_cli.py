@@ -79,7 +79,7 @@ def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
     sph = cmd[cmd.index("--sphere"):]
     assert subprocess.run(base + ["-p", xml, "--steps", "4", "--dump", dump] + sph, capture_output=True).returncode == 0
     assert subprocess.run(base + ["-p", xml, "--steps", "2", "--save-state", ck] + sph, capture_output=True).returncode == 0
-    assert open(ck, "rb").read(8) == b"PBFCKPT1"
+    assert open(ck, "rb").read(8) == b"PBFCKPT2"
     r = subprocess.run(base + ["--load-state", ck, "--steps", "2", "--dump", dump2], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     d4, d22 = read_dump(dump), read_dump(dump2)
@@ -87,6 +87,22 @@ def test_cli_run_equals_python_api_and_tracks_reference(tmp_path):
     open(ck, "r+b").write(b"NOTACKPT")
     r = subprocess.run(base + ["--load-state", ck, "--steps", "1"], capture_output=True, text=True)
     assert r.returncode == 1 and "checkpoint error" in r.stdout
+    # obstacle triangles travel in the restart file too: 2 + 2 steps without --tris on the second leg == 4 steps
+    import helpers as H
+    keep = sref["pos"][:, 1] >= 0.6
+    _write_xml(xml, sref["pos"][keep], sref["vel"][keep], float(sref["rho0"]))
+    trif = str(tmp_path / "mesh.tris")
+    H.write_tris(trif, H.uv_sphere_mesh((-0.5, 0.3, 0.5), 0.25, 10, 20))
+    assert subprocess.run(base + ["-p", xml, "--steps", "4", "--dump", dump, "--tris", trif], capture_output=True).returncode == 0
+    assert subprocess.run(base + ["-p", xml, "--steps", "2", "--save-state", ck, "--tris", trif], capture_output=True).returncode == 0
+    r = subprocess.run(base + ["--load-state", ck, "--steps", "2", "--dump", dump2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d4, d22 = read_dump(dump), read_dump(dump2)
+    assert np.array_equal(d4[3]["state"][:, :7], d22[1]["state"][:, :7])
+    r = subprocess.run(base + ["--load-state", ck, "--steps", "1", "--iterations", "4"], capture_output=True, text=True)
+    assert r.returncode == 2 and "--iterations" in r.stdout
+    r = subprocess.run([exe, "--load-state", ck, "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 2
     _write_xml(xml, ref["pos"], ref["vel"], float(ref["rho0"]))
     # -d 0.05 => ceil(0.05/0.016) = 4 steps (while simulate_time < T, Q18)
     r = subprocess.run([exe, "-p", xml, "-d", "0.05", "--quiet"], capture_output=True, text=True)
@@ -117,3 +133,44 @@ def test_cli_surface_equals_python_api(tmp_path):
     assert nt > 500 and abs(nt - len(fx["tris"])) < 0.5 * len(fx["tris"])     # same scene, 3 vs 12 steps: same order of magnitude
     nrm = np.linalg.norm(tris[:, 9:12], axis=1)
     assert np.all((np.abs(nrm - 1) < 1e-9) | (nrm == 0))
+
+
+@pytest.mark.gpu
+def test_cli_neighbor_count_warnings(tmp_path):
+    """Particle::initializeWithNewNeighbors (particles.cpp:165-173) warns on cerr about every particle with fewer than
+    18 neighbours; the adapter prints the same lines (first 128 in index order, then a summary) from the counts the
+    neighbour build leaves on the device.  p.xml (spacing 0.15): the reference prints 100 such lines per step."""
+    exe = _build()
+    sc = np.load(os.path.join(GOLDEN, "scene_p.npz")); ref = np.load(os.path.join(GOLDEN, "ref_p.npz"))
+    xml = str(tmp_path / "p.xml")
+    _write_xml(xml, sc["pos"], sc["vel"], float(sc["rho0"]))
+    r = subprocess.run([exe, "-p", xml, "--steps", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stderr.splitlines() if " only has " in l and l.startswith("P(p(")]
+    from fluid_b200 import api
+    g = api.Solver(api.default_params(rest_density=float(sc["rho0"])))
+    g.upload(sc["pos"], sc["vel"]); g.estimate_densities(); g.capture(True); g.step(1)
+    _, cnt = g.neighbor_digest()
+    low = np.flatnonzero(cnt < 18)
+    more = [l for l in r.stderr.splitlines() if "more particles with fewer than 18" in l]
+    shown = len(lines)
+    assert shown == len(low) if len(low) <= 128 else (0 < shown <= 128 and int(more[0].split("and ")[1].split()[0]) == len(low) - shown)
+    assert len(low) == int(np.count_nonzero(ref["nbr_counts_0"] < 18))        # the unmodified reference's own count for this step
+    xp = g.array(3)                                                            # PBF_ARRAY_XPRED
+    for l, i in zip(lines, low[:shown]):
+        assert l.endswith(f" only has {cnt[i]} neighbors.")
+        x = [float(t) for t in l[len("P(p("):l.index("),v(")].split(",")]
+        assert np.allclose(x, xp[i], rtol=1e-5, atol=1e-6)                     # 6 significant digits on the stream
+    # the C ABI itself: a deterministic prefix (by id) of the records, the total beyond the cap still counted
+    import ctypes as C
+    lib = api.load_library()
+    lib.pbf_set_neighbor_alert.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+    lib.pbf_get_neighbor_alerts.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    assert lib.pbf_set_neighbor_alert(g.h, 18, 16) == 0
+    g.upload(sc["pos"], sc["vel"]); g.step(1)
+    ids = np.zeros(16, dtype=np.uint32); cn = np.zeros(16, dtype=np.uint32); tot = C.c_size_t(); wr = C.c_size_t()
+    assert lib.pbf_get_neighbor_alerts(g.h, 16, ids.ctypes.data_as(C.c_void_p), cn.ctypes.data_as(C.c_void_p), None, None, C.byref(wr), C.byref(tot)) == 0
+    _, cnt2 = g.neighbor_digest()
+    low2 = np.flatnonzero(cnt2 < 18)
+    m = wr.value
+    assert tot.value == len(low2) and 0 < m <= 16 and np.array_equal(ids[:m], low2[:m]) and np.array_equal(cn[:m], cnt2[ids[:m]])
