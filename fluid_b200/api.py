@@ -242,6 +242,112 @@ class Solver:
         return {names[i].decode(): (ms[i], int(ln[i])) for i in range(k)}
 
 
+def _bind_multi(lib):
+    if getattr(lib, "_multi_bound", False):
+        return lib
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    sig = {
+        "pbf_create_multi": (i32, [C.POINTER(PbfParams), i32, vp, C.POINTER(vp)]),
+        "pbf_multi_destroy": (None, [vp]),
+        "pbf_multi_last_error": (C.c_char_p, [vp]),
+        "pbf_multi_num_devices": (i32, [vp]),
+        "pbf_multi_set_obstacle_spheres": (i32, [vp, sz, vp]),
+        "pbf_multi_set_obstacle_triangles": (i32, [vp, sz, vp]),
+        "pbf_multi_upload": (i32, [vp, sz, vp, vp]),
+        "pbf_multi_step": (i32, [vp, i32]),
+        "pbf_multi_sync": (i32, [vp]),
+        "pbf_multi_download": (i32, [vp, vp, vp, vp]),
+        "pbf_multi_num_particles": (sz, [vp]),
+        "pbf_multi_stats": (i32, [vp, vp, vp, vp]),
+        "pbf_multi_set_rebalance": (i32, [vp, i32, C.c_double]),
+        "pbf_multi_plan": (i32, [vp, vp, vp, vp]),
+        "pbf_multi_neighbor_digest": (i32, [vp, vp, vp]),
+        "pbf_multi_launch_count": (u64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._multi_bound = True
+    return lib
+
+
+class MultiSolver:
+    """One pbf_multi handle (include/pbf_b200_multi.h): x-slabs on several GPUs driven by this process, peer-mode halos.
+    `devices` may name a device more than once (several slabs on one GPU: how the 1-GPU test box exercises the path)."""
+
+    def __init__(self, params=None, devices=(0,)):
+        self.lib = _bind_multi(load_library())
+        self.params = params if params is not None else default_params()
+        ids = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.pbf_create_multi(C.byref(self.params), len(devices), ids, C.byref(h))
+        if rc != PBF_OK:
+            raise PbfError(rc, "pbf_create_multi failed (no CUDA device?)" if rc == PBF_ERR_NO_DEVICE else "pbf_create_multi failed")
+        self.h = h
+        self.n = 0
+        self.world = len(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pbf_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != PBF_OK:
+            raise PbfError(rc, self.lib.pbf_multi_last_error(self.h).decode())
+
+    def set_obstacle_spheres(self, spheres):
+        sp = np.ascontiguousarray(spheres, dtype=np.float64).reshape(-1, 4)
+        self._ck(self.lib.pbf_multi_set_obstacle_spheres(self.h, sp.shape[0], _ptr(sp)))
+
+    def set_obstacle_triangles(self, tris):
+        t = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 18)
+        self._ck(self.lib.pbf_multi_set_obstacle_triangles(self.h, t.shape[0], _ptr(t)))
+
+    def set_rebalance(self, every_k_steps=8, threshold=1.05):
+        self._ck(self.lib.pbf_multi_set_rebalance(self.h, every_k_steps, threshold))
+
+    def upload(self, pos, vel):
+        pos = np.ascontiguousarray(pos, dtype=np.float64); vel = np.ascontiguousarray(vel, dtype=np.float64)
+        self.n = pos.shape[0]
+        self._ck(self.lib.pbf_multi_upload(self.h, self.n, _ptr(pos), _ptr(vel)))
+
+    def step(self, n_steps=1, sync=True):
+        self._ck(self.lib.pbf_multi_step(self.h, n_steps))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._ck(self.lib.pbf_multi_sync(self.h))
+
+    def download(self):
+        P = np.empty((self.n, 3)); V = np.empty((self.n, 3)); R = np.empty(self.n)
+        self._ck(self.lib.pbf_multi_download(self.h, _ptr(P), _ptr(V), _ptr(R)))
+        return P, V, R
+
+    def stats(self):
+        a, b, ms = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.pbf_multi_stats(self.h, C.byref(a), C.byref(b), C.byref(ms)))
+        return a.value, b.value, ms.value
+
+    def neighbor_digest(self):
+        d = np.empty(self.n, dtype=np.uint64); c = np.empty(self.n, dtype=np.uint32)
+        self._ck(self.lib.pbf_multi_neighbor_digest(self.h, _ptr(d), _ptr(c)))
+        return d, c
+
+    def plan(self):
+        """(column boundaries, owned particles per device, number of re-balancing moves so far)"""
+        b = np.zeros(self.world + 1, dtype=np.int32); o = np.zeros(self.world, dtype=np.uint64); k = C.c_uint64()
+        self._ck(self.lib.pbf_multi_plan(self.h, _ptr(b), _ptr(o), C.byref(k)))
+        return b, o, int(k.value)
+
+    def launch_count(self):
+        return int(self.lib.pbf_multi_launch_count(self.h))
+
+
 class Particles:
     """Python mirror of the reference's `struct Particles` (src/particles.h:105-140) backed by the
     GPU solver: same member names, argument meaning and call order as the reference host code

@@ -162,6 +162,9 @@ int check_device_errors(pbf_handle* h) {
     if (s.err & ERRBIT_MIGRATION) return fail(h, PBF_ERR_DOMAIN, "particle left its slab by more than one cell column in one step");
     if (s.err & ERRBIT_NBR_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "neighbour list capacity exceeded (raise PBF_NBR_ROWS); results of this step are invalid");
     if (s.err & ERRBIT_HALO_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "halo / migration buffer capacity exceeded");
+    if (s.err & ERRBIT_SLAB_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded (owned + ghost particles > particle_cap)");
+    if (s.err & ERRBIT_PEER_TIMEOUT) return fail(h, PBF_ERR_CUDA, "peer mode: a neighbouring slab did not reach the exchange point in time");
+    if (s.err & ERRBIT_PEER_MISMATCH) return fail(h, PBF_ERR_DOMAIN, "peer mode: boundary column and the neighbour's ghost range differ in length");
     return fail(h, PBF_ERR_CUDA, "unknown device error flag");
   }
   return PBF_OK;
@@ -268,6 +271,10 @@ void pbf_destroy(pbf_handle* h) {
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); for (int k = 0; k < 4; k++) if (h->ev_rb[k]) cudaEventDestroy(h->ev_rb[k]); }
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
+  for (int k = 0; k < 2; k++) if (h->peer[k].ipc) for (void* p : h->peer[k].ipc_base) if (p) cudaIpcCloseMemHandle(p);
+  cudaFree(h->link); cudaFree(h->col_hist);
+  if (h->col_hist_host) cudaFreeHost(h->col_hist_host);
+  if (h->ev_hist) cudaEventDestroy(h->ev_hist);
   delete static_cast<HandleExtra*>(h->host_extra);
   cudaFree(h->tri_dev); cudaFree(h->bvh_dev); cudaFree(h->tri_id_dev); cudaFree(h->alert_buf);
   delete h;

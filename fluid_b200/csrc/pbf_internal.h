@@ -11,7 +11,21 @@
 
 namespace pbf {
 
-enum { ERRBIT_NBR_CAPACITY = 1, ERRBIT_NONFINITE = 2, ERRBIT_HALO_CAPACITY = 4, ERRBIT_MIGRATION = 8 };
+enum { ERRBIT_NBR_CAPACITY = 1, ERRBIT_NONFINITE = 2, ERRBIT_HALO_CAPACITY = 4, ERRBIT_MIGRATION = 8,
+       ERRBIT_SLAB_CAPACITY = 16, ERRBIT_PEER_TIMEOUT = 32, ERRBIT_PEER_MISMATCH = 64 };
+
+// Device-resident description of a slab handle's sorted arrays plus what its x-neighbours need to see of it (peer mode,
+// include/pbf_b200_multi.h).  Written on the device after every sort, so the host never needs the counts and a step has no
+// host round trip; the neighbours read b[] and write flag[] through peer-mapped pointers (same process: peer access,
+// other process: CUDA IPC).
+struct SlabLink {
+  uint32_t b[8];          // b0, b1, b2, b3, n_sorted of the LAST sort: [0,b0) left ghosts | [b0,b3) owned | [b3,n) right ghosts
+  uint32_t nb[2][8];      // copies of the x-neighbours' b[] for the same step (k_fetch_peer_ranges): [0] left, [1] right
+  uint32_t flag[2];       // last epoch completed by the left [0] / right [1] neighbour (written by ITS k_signal)
+  uint32_t col_hist_valid, pad[5];
+};
+// where a solver pass also stores its boundary columns: the neighbours' ghost ranges of the same array (peer stores)
+struct PushArgs { float4* dst[2]; };
 
 // device-resident scalars (one allocation)
 struct Scalars {
@@ -62,6 +76,24 @@ struct Solver {
   float4 *ghost_send[2] = {nullptr, nullptr}, *ghost_recv[2] = {nullptr, nullptr};
   uint32_t bounds[5] = {0, 0, 0, 0, 0};   // b0..b3, n_sorted of the last slab sort (see pbf_b200_slab.h)
   size_t n_in_cap() const { return slab ? cap : 0; }
+  size_t append_base = 0;            // slab: immigrants / ghosts are appended at append_base + {0,1,2,3} * halo_cap (= particle_cap)
+  int max_cols = 0;                  // slab: the cell arrays hold this many owned columns (+2 ghost columns): room for re-balancing
+  // peer mode (pbf_b200_multi.h): device-side ranges, peer stores, flag synchronisation, no host sync inside a step
+  bool p2p = false;
+  SlabLink* link = nullptr;          // this handle's link block (device memory, visible to the neighbours)
+  struct Peer {
+    SlabLink* link = nullptr;        // the neighbour's link block
+    float4 *xs_a = nullptr, *xs_b = nullptr, *xs_w = nullptr;     // its solver arrays (ghost ranges are written by us)
+    float4 *mig_recv = nullptr, *ghost_recv = nullptr;           // its receive buffers for OUR side
+    bool ipc = false;                // mapped with cudaIpcOpenMemHandle (closed in pbf_destroy)
+    void* ipc_base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  } peer[2];                         // [0] left, [1] right
+  uint32_t epoch = 0;                // signals issued so far (identical sequence on every rank)
+  long long wait_timeout_ns = 20000000000ll;
+  uint32_t* col_hist = nullptr;      // owned particles per global cell column after the last sort (re-balancing), device
+  uint32_t* col_hist_host = nullptr; // ... its pinned host copy
+  cudaEvent_t ev_hist = nullptr;
+  long long hist_step = -1;          // step index (steps_done at its sort) of the histogram in flight / delivered
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)
   void* host_extra = nullptr;        // pbf_api.cu's HandleExtra (pinned staging, registered host ranges)

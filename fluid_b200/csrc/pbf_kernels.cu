@@ -17,6 +17,18 @@ static constexpr uint32_t CELL_INVALID = 0xFFFFFFFFu;
 
 __device__ __forceinline__ float3 xyz(const float4& v) { return make_float3(v.x, v.y, v.z); }
 
+// Peer mode: the ranges of the sorted arrays live on the device (SlabLink::b), launches are sized for the capacity, and
+// a pass that produces values its x-neighbours gather as ghosts stores them straight into the neighbours' arrays
+// (peer-mapped pointers over NVLink): the owner's boundary column and the neighbour's ghost range have the same order
+// (include/pbf_b200_slab.h), so entry t of the left boundary column goes to entry b3' + t of the left neighbour and
+// entry k of the right boundary column to entry k of the right neighbour.  lk == nullptr: ranges by value, no push.
+__device__ __forceinline__ void push_boundary(const SlabLink* __restrict__ lk, const PushArgs& pa, uint32_t t, float4 v) {
+  if (lk == nullptr) return;
+  const uint32_t cnt = lk->b[3] - lk->b[0], nl = lk->b[1] - lk->b[0], nr = lk->b[3] - lk->b[2];
+  if (pa.dst[0] != nullptr && t < nl) pa.dst[0][lk->nb[0][3] + t] = v;
+  if (pa.dst[1] != nullptr && t >= cnt - nr) pa.dst[1][t - (cnt - nr)] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // A. predict + collide + hash      (applyForceVelocity + clamp_response, particles.cpp:175-183,87-132)
 // EXACT regime: x* is bit-identical to the fp32 oracle.
@@ -31,8 +43,9 @@ k_predict_hash(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, con
                float4* __restrict__ vel, const uint32_t* __restrict__ orig, float4* __restrict__ xs_tmp,
                uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count,
                int apply_forces, float4* __restrict__ mig_left, float4* __restrict__ mig_right, uint32_t mig_cap,
-               Scalars* __restrict__ sc) {
+               Scalars* __restrict__ sc, const SlabLink* __restrict__ lk) {
   const uint32_t t = blockIdx.x * TPB + threadIdx.x;
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }            // owned range of the previous sort
   if (t >= n) return;
   const uint32_t i = i0 + t;
   const float4 x = pos[i];
@@ -277,7 +290,9 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
                   const float4* __restrict__ xs,
                   const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ nbr,
                   uint32_t* __restrict__ slice_off, uint32_t* __restrict__ nbr_cnt,
-                  unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc, int use_per_lane) {
+                  unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc, int use_per_lane,
+                  const SlabLink* __restrict__ lk) {
+  if (lk) { i0 = lk->b[0]; cnt_range = lk->b[3] - lk->b[0]; sentinel = lk->b[4]; }
   const uint32_t t = blockIdx.x * TPB + threadIdx.x;     // index inside the owned range
   const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
@@ -444,8 +459,9 @@ k_neighbor_alert(uint32_t n, uint32_t thr, const uint32_t* __restrict__ nbr_cnt,
 }
 
 // the sentinel particle (index n): far outside every support radius, zero velocity / vorticity
-__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega, float4* xv) {
+__global__ void k_set_sentinel(uint32_t n, float4* a, float4* b, float4* w, float4* vtmp, float4* omega, float4* xv, const SlabLink* lk) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (lk) n = lk->b[4];
     xv[2 * (size_t)n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     xv[2 * (size_t)n + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     a[n] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
@@ -494,7 +510,7 @@ __device__ __forceinline__ float block_sum_to_double(float v, double* target) {
 __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t, uint32_t i, const float4* __restrict__ xs_in,
                                                  float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr,
                                                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
-                                                 float* __restrict__ rho_out) {
+                                                 float* __restrict__ rho_out, const SlabLink* __restrict__ lk, const PushArgs& push) {
   const float4 pi = xs_in[i];
   float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
 #define BODY_L(J)                                                          \
@@ -515,7 +531,9 @@ __device__ __forceinline__ float lambda_particle(const DevParams& P, uint32_t t,
   const float denom = gs * gs * dsum + (Gx * Gx + Gy * Gy + Gz * Gz);
   const float c_i = rho * P.inv_rho0 - 1.f;              // not clamped at 0 (Q7)
   const float lambda = -c_i / (denom + P.eps_relax);
-  xs_out[i] = make_float4(pi.x, pi.y, pi.z, lambda);
+  const float4 out = make_float4(pi.x, pi.y, pi.z, lambda);
+  xs_out[i] = out;
+  push_boundary(lk, push, t, out);                       // (x*, lambda) of the boundary columns -> the neighbours' ghost ranges
   if (rho_out) rho_out[i] = rho;
   return rho;
 }
@@ -536,10 +554,12 @@ __global__ void __launch_bounds__(TPB)      // 40 registers, 6 CTAs per SM; forc
 k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multiple of 32 */, uint32_t n /* end of the t range */,
          const float4* __restrict__ xs_in,
          float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
-         const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum) {
+         const uint32_t* __restrict__ nbr_cnt, float* __restrict__ rho_out, double* __restrict__ rho_sum,
+         const SlabLink* __restrict__ lk, const PushArgs push) {
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }
   const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   float rho = 0.f;
-  if (t < n) rho = lambda_particle(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out);
+  if (t < n) rho = lambda_particle(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out, lk, push);
   if (rho_sum) block_sum_to_double(rho, rho_sum);
 }
 
@@ -551,7 +571,8 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multip
 template <int NCORR, bool SPH>
 __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, uint32_t i, const float4* __restrict__ xs_in,
                                                float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr,
-                                               const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt) {
+                                               const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
+                                               const SlabLink* __restrict__ lk, const PushArgs& push) {
   const float4 pi = xs_in[i];
   float ax = 0.f, ay = 0.f, az = 0.f;
 #define BODY_D(J)                                                          \
@@ -572,17 +593,20 @@ __device__ __forceinline__ void delta_particle(const DevParams& P, uint32_t t, u
   const float sc = P.spiky_c * P.inv_rho0;
   const float3 dp = make_float3(sc * ax, sc * ay, sc * az);
   const float3 p = ex_collide<SPH>(P, make_float3(pi.x, pi.y, pi.z), dp, false);
-  xs_out[i] = make_float4(p.x, p.y, p.z, 0.f);
+  const float4 out = make_float4(p.x, p.y, p.z, 0.f);
+  xs_out[i] = out;
+  push_boundary(lk, push, t, out);
 }
 
 template <int NCORR, bool SPH>
 __global__ void __launch_bounds__(TPB, SPH ? 6 : 1)   // obstacle instantiation: capped at 40 registers = 6 CTAs per SM like the box-only one (38)
 k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t n, const float4* __restrict__ xs_in,
         float4* __restrict__ xs_out, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
-        const uint32_t* __restrict__ nbr_cnt) {
+        const uint32_t* __restrict__ nbr_cnt, const SlabLink* __restrict__ lk, const PushArgs push) {
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }
   const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   if (t >= n) return;
-  delta_particle<NCORR, SPH>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt);
+  delta_particle<NCORR, SPH>(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, lk, push);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,8 +618,9 @@ k_delta(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, uint32_t 
 // cost 2x (scripts/ubench/ffma2.cu, profiles/r01_ubench_ffma2_gather.txt).
 __global__ void __launch_bounds__(TPB)
 k_velocity(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs,
-           const float4* __restrict__ pos, float4* __restrict__ vtmp, float4* __restrict__ xv) {
+           const float4* __restrict__ pos, float4* __restrict__ vtmp, float4* __restrict__ xv, const SlabLink* __restrict__ lk) {
   const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (lk) n = lk->b[4];
   if (i >= n) return;
   const float4 a = xs[i], b = pos[i];
   const float4 v = make_float4(P.inv_dt * (a.x - b.x), P.inv_dt * (a.y - b.y), P.inv_dt * (a.z - b.z), 0.f);
@@ -616,7 +641,8 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, 
                  float4* __restrict__ xs_w, const float4* __restrict__ vtmp, const float4* __restrict__ xv, float4* __restrict__ vel_out, float4* __restrict__ omega,
                  float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
                  const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
-                 double* __restrict__ rho_sum) {
+                 double* __restrict__ rho_sum, const SlabLink* __restrict__ lk, const PushArgs push) {
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }
   const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   float rho = 0.f;
@@ -645,6 +671,7 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, 
     const float on = sqrtf(ox * ox + oy * oy + oz * oz);
     omega[i] = make_float4(ox, oy, oz, on);
     xs_w[i] = make_float4(pi.x, pi.y, pi.z, on);        // (x*, |omega|): ONE 16-byte gather per pair in the confinement pass
+    push_boundary(lk, push, t, make_float4(pi.x, pi.y, pi.z, on));
     const float xc = P.enable_xsph ? P.visc_c * P.poly6_c : 0.f;   // v += C * sum v_ij W  (not density-normalised, Q12)
     vel_out[i] = make_float4(fmaf(xc, sx, vi.x), fmaf(xc, sy, vi.y), fmaf(xc, sz, vi.z), 0.f);
     rho_out[i] = rho;                                              // the density the visualiser reads
@@ -656,7 +683,8 @@ __global__ void __launch_bounds__(TPB)
 k_confine_commit(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs /* (x*, |omega|) */,
                  const float4* __restrict__ omega, float4* __restrict__ vel, float4* __restrict__ pos,
                  const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
-                 const uint32_t* __restrict__ nbr_cnt) {
+                 const uint32_t* __restrict__ nbr_cnt, const SlabLink* __restrict__ lk) {
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }
   const uint32_t t = tile_of_block(P) * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   if (t >= n) return;
@@ -885,6 +913,17 @@ k_neighbor_digest(uint32_t i0, uint32_t n, const uint32_t* __restrict__ nbr, con
 // launch sequence
 // ------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(size_t n, int per_block = TPB) { return (unsigned)((n + per_block - 1) / per_block); }
+// Peer mode: the counts live on the device, so launches are sized for the capacity (blocks beyond the real count exit
+// at once) and the kernels read the ranges from the link block.
+static inline const SlabLink* link_of(const Solver* h) { return h->p2p ? h->link : nullptr; }
+static inline size_t owned_ub(const Solver* h) { return h->p2p ? h->append_base : h->r_cnt; }
+static inline size_t sorted_ub(const Solver* h) { return h->p2p ? h->append_base : h->n_sorted; }
+static inline PushArgs push_to(const Solver* h, int which /*0 xs_a, 1 xs_b, 2 xs_w*/) {
+  PushArgs pa; pa.dst[0] = pa.dst[1] = nullptr;
+  if (!h->p2p) return pa;
+  for (int s = 0; s < 2; s++) pa.dst[s] = which == 0 ? h->peer[s].xs_a : (which == 1 ? h->peer[s].xs_b : h->peer[s].xs_w);
+  return pa;
+}
 
 #define LAUNCH(h, kid, kern, grid, ...)                                   \
   do {                                                                    \
@@ -898,6 +937,11 @@ static inline unsigned blocks_for(size_t n, int per_block = TPB) { return (unsig
 
 // Phase 1 of the sort: clear the histogram, predict the owned range [r_i0, r_i0 + r_cnt) of the
 // current buffers (or just re-bin committed positions when apply_forces == 0) and hash it.
+// where emigrants / ghosts for side s are packed: the own send buffer (a host driver moves it), or in peer mode the
+// neighbour's receive buffer itself
+static inline float4* mig_out(const Solver* h, int s) { return h->p2p ? h->peer[s].mig_recv : h->mig_send[s]; }
+static inline float4* ghost_out(const Solver* h, int s) { return h->p2p ? h->peer[s].ghost_recv : h->ghost_send[s]; }
+
 void enqueue_predict_hash(Solver* h, int apply_forces) {
   const int cur = h->cur;
   // every path that re-sorts (step, estimate_densities, re-binning for the density field / surfacer) starts here: the
@@ -908,9 +952,9 @@ void enqueue_predict_hash(Solver* h, int apply_forces) {
   cudaMemsetAsync(&h->sc->nbr_cursor, 0, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(h->sc->counters, 0, sizeof(h->sc->counters), h->stream);
 #define LAUNCH_PREDICT(KERN)                                                                                                      \
-  LAUNCH(h, K_PREDICT, KERN, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur], h->xs_tmp, h->cell_of, \
-         h->rank, h->cell_count, apply_forces, h->slab && h->has_left ? h->mig_send[0] : (float4*)nullptr,                            \
-         h->slab && h->has_right ? h->mig_send[1] : (float4*)nullptr, (uint32_t)h->halo_cap, h->sc)
+  LAUNCH(h, K_PREDICT, KERN, blocks_for(owned_ub(h)), h->dp, h->r_i0, h->r_cnt, h->pos[cur], h->vel[cur], h->orig[cur], h->xs_tmp, h->cell_of, \
+         h->rank, h->cell_count, apply_forces, h->slab && h->has_left ? mig_out(h, 0) : (float4*)nullptr,                            \
+         h->slab && h->has_right ? mig_out(h, 1) : (float4*)nullptr, (uint32_t)h->halo_cap, h->sc, link_of(h))
   if (h->dp.n_sph > 0 || h->dp.n_tri > 0) LAUNCH_PREDICT(k_predict_hash<true>); else LAUNCH_PREDICT(k_predict_hash<false>);
 #undef LAUNCH_PREDICT
 }
@@ -942,18 +986,18 @@ static int nb_per_lane() {      // PBF_NB_PER_LANE=1: the per-lane candidate wal
 // Phase 3: frozen neighbour lists for the range [r_i0, r_i0 + r_cnt) of the n_sorted sorted particles.
 void enqueue_build(Solver* h, int include_self) {
   h->prof_begin(K_REORDER);
-  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega, h->xv);
+  k_set_sentinel<<<1, 32, 0, h->stream>>>(h->n_sorted, h->xs_a, h->xs_b, h->xs_tmp, h->vtmp, h->omega, h->xv, link_of(h));
   h->prof_end(K_REORDER); h->launches++;
-  LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
-         h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc, nb_per_lane());
+  LAUNCH(h, K_NEIGHBORS, k_build_neighbors, blocks_for(owned_ub(h)), h->dp, h->r_i0, h->r_cnt, h->n_sorted, h->xs_a, h->cell_start,
+         h->nbr, h->slice_off, h->nbr_cnt, (unsigned long long)h->nbr_cap_rows, include_self, h->sc, nb_per_lane(), link_of(h));
 }
 
 // Sub-ranges of the owned range for overlapping halo exchange with compute (slab mode):
 // PART_BOUNDARY = the first / last owned cell column rounded outwards to whole slices (what the
 // x-neighbours need as ghosts), PART_INTERIOR = the rest, PART_ALL = everything.
 static int part_ranges(const Solver* h, int part, uint32_t rng[2][2]) {
-  const uint32_t cnt = h->r_cnt;
-  if (part == PART_ALL || !h->slab) { rng[0][0] = 0; rng[0][1] = cnt; return part == PART_INTERIOR ? 0 : 1; }
+  const uint32_t cnt = (uint32_t)owned_ub(h);
+  if (part == PART_ALL || !h->slab || h->p2p) { rng[0][0] = 0; rng[0][1] = cnt; return part == PART_INTERIOR ? 0 : 1; }
   const uint32_t nl = h->has_left ? h->bounds[1] - h->bounds[0] : 0u, nr = h->has_right ? h->bounds[3] - h->bounds[2] : 0u;
   uint32_t l_end = std::min(cnt, (nl + 31u) & ~31u), r_begin = (cnt - std::min(cnt, nr)) & ~31u;
   if (r_begin < l_end) r_begin = l_end;                   // thin slab: the two boundary parts meet
@@ -969,14 +1013,14 @@ void enqueue_lambda(Solver* h, int first_iter, int part) {
   const int k = part_ranges(h, part, rng);
   for (int q = 0; q < k; q++)
     LAUNCH(h, K_LAMBDA, k_lambda, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_b, h->nbr,
-           h->slice_off, h->nbr_cnt, (float*)nullptr, first_iter ? &h->sc->rho_first : (double*)nullptr);
+           h->slice_off, h->nbr_cnt, (float*)nullptr, first_iter ? &h->sc->rho_first : (double*)nullptr, link_of(h), push_to(h, 1));
 }
 void enqueue_delta(Solver* h, int part) {
   uint32_t rng[2][2];
   const int k = part_ranges(h, part, rng);
   for (int q = 0; q < k; q++) {
     const unsigned g = blocks_for(rng[q][1] - rng[q][0]);
-#define LAUNCH_DELTA(KERN) LAUNCH(h, K_DELTA, KERN, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt)
+#define LAUNCH_DELTA(KERN) LAUNCH(h, K_DELTA, KERN, g, h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_b, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, link_of(h), push_to(h, 0))
     const bool sph = h->dp.n_sph > 0 || h->dp.n_tri > 0;   // box-only scenes run the instantiation without the obstacle code
     if (h->dp.n_corr == 4) { if (sph) LAUNCH_DELTA((k_delta<4, true>)); else LAUNCH_DELTA((k_delta<4, false>)); }
     else { if (sph) LAUNCH_DELTA((k_delta<-1, true>)); else LAUNCH_DELTA((k_delta<-1, false>)); }
@@ -984,14 +1028,14 @@ void enqueue_delta(Solver* h, int part) {
   }
 }
 void enqueue_velocity(Solver* h) {   // every sorted particle, ghosts included (their x and x* are bit-identical to the owner's)
-  LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(h->n_sorted), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp, h->xv);
+  LAUNCH(h, K_VELOCITY, k_velocity, blocks_for(sorted_ub(h)), h->dp, h->n_sorted, h->xs_a, h->pos[h->cur], h->vtmp, h->xv, link_of(h));
 }
 void enqueue_vorticity(Solver* h, int part) {
   uint32_t rng[2][2];
   const int k = part_ranges(h, part, rng);
   for (int q = 0; q < k; q++)
     LAUNCH(h, K_VORT_XSPH, k_vorticity_xsph, blocks_for(rng[q][1] - rng[q][0]), h->dp, h->r_i0, rng[q][0], rng[q][1], h->xs_a, h->xs_tmp, h->vtmp, h->xv,
-           h->vel[h->cur], h->omega, h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final);
+           h->vel[h->cur], h->omega, h->rho, h->nbr, h->slice_off, h->nbr_cnt, &h->sc->rho_final, link_of(h), push_to(h, 2));
 }
 // velocity + XSPH + vorticity in the reference's sequential order, by fixed-point sweeps (single GPU)
 void enqueue_vorticity_reference_order(Solver* h) {
@@ -1015,8 +1059,8 @@ void enqueue_vorticity_reference_order(Solver* h) {
 }
 
 void enqueue_confine(Solver* h) {
-  LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(h->r_cnt), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
-         h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt);
+  LAUNCH(h, K_CONFINE, k_confine_commit, blocks_for(owned_ub(h)), h->dp, h->r_i0, h->r_cnt, h->xs_tmp, h->omega, h->vel[h->cur],
+         h->pos[h->cur], h->nbr, h->slice_off, h->nbr_cnt, link_of(h));
 }
 
 // single-GPU step: every particle is owned, n never changes, nothing needs a host round trip

@@ -1,6 +1,12 @@
-"""x-slab decomposition of the PBF step over the GPUs of one box: one process per GPU, migration
-and ghost-particle halo exchange between x-adjacent ranks over NCCL (torch.distributed is the
-plumbing; every kernel is in libpbf_b200.so, C ABI include/pbf_b200_slab.h).
+"""x-slab decomposition of the PBF step over the GPUs of one box: one process per GPU (the driver of the
+single-process form is pbf_create_multi, include/pbf_b200_multi.h); every kernel is in libpbf_b200.so, C ABI
+include/pbf_b200_slab.h.  Two transports between x-adjacent ranks:
+  "p2p"   (default with one GPU per rank) peer mode of the library: CUDA IPC maps the neighbours' buffers once, then
+          migration / ghost messages and the per-iteration boundary values are stored straight into the neighbours'
+          memory by the kernels that produce them and hand-overs are flag words; a step is ONE library call with no
+          host synchronisation, torch.distributed only carries the IPC handles and the re-balancing histogram;
+  "nccl"  the host-driven protocol below with torch.distributed send/recv of device ranges (and "staged": the same
+          through host copies, for gloo).
 
 Protocol per step (the reference is single-process, particles.cpp:250-297):
   predict -> exchange emigrants -> absorb + pack ghost layers -> exchange ghosts -> sort + neighbour
@@ -32,6 +38,18 @@ def _bind(lib):
         "pbf_cell_columns": (i32, [C.POINTER(api.PbfParams), sz, vp, vp]),
         "pbf_set_stream": (i32, [vp, vp]),
         "pbf_slab_configure": (i32, [vp, i32, i32, i32, i32, sz, sz]),
+        "pbf_slab_configure_ex": (i32, [vp, i32, i32, i32, i32, sz, sz, i32]),
+        "pbf_slab_set_columns": (i32, [vp, i32, i32, i32, i32]),
+        "pbf_slab_columns": (i32, [vp, C.POINTER(C.c_int * 4)]),
+        "pbf_slab_column_histogram": (i32, [vp, vp, sz, i32, C.POINTER(C.c_longlong)]),
+        "pbf_slab_p2p_blob_size": (sz, []),
+        "pbf_slab_p2p_export": (i32, [vp, vp]),
+        "pbf_slab_p2p_connect_ipc": (i32, [vp, vp, vp]),
+        "pbf_slab_set_wait_timeout": (i32, [vp, C.c_double]),
+        "pbf_slab_step_p2p": (i32, [vp, i32]),
+        "pbf_slab_refresh_ranges": (i32, [vp, C.POINTER(C.c_uint32 * 5)]),
+        "pbf_partition_columns": (i32, [vp, i32, i32, vp]),
+        "pbf_plan_rebalance": (i32, [vp, i32, i32, vp, C.c_uint64, C.c_double, vp, C.POINTER(C.c_double)]),
         "pbf_slab_upload": (i32, [vp, sz, vp, vp, vp]),
         "pbf_slab_download": (i32, [vp, sz, vp, vp, vp, vp, C.POINTER(sz)]),
         "pbf_slab_neighbor_digest": (i32, [vp, sz, vp, vp]),
@@ -118,7 +136,8 @@ class _DevMem:
 class SlabSolver:
     """One rank of the slab-decomposed solver."""
 
-    def __init__(self, params, rank, world, device=0, halo_factor=4.0, staged=None, overlap=None):
+    def __init__(self, params, rank, world, device=0, halo_factor=4.0, staged=None, overlap=None, transport=None,
+                 rebalance_every=8, rebalance_threshold=1.05, cap_factor=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -147,6 +166,19 @@ class SlabSolver:
         want = os.environ.get("PBF_SLAB_OVERLAP", "0") == "1" if overlap is None else overlap
         self.overlap = bool(want) and world > 1 and not self.staged
         self.comm_stream = torch.cuda.Stream(device=device) if self.overlap else None
+        # transport: "p2p" = the library's peer mode (CUDA IPC between the ranks' processes)
+        t = transport or os.environ.get("PBF_SLAB_TRANSPORT")
+        if t is None:
+            t = "p2p" if (world == 1 or not self.staged) and not self.overlap else ("staged" if self.staged else "nccl")
+        assert t in ("p2p", "nccl", "staged"), t
+        self.transport = t
+        if t == "staged":
+            self.staged = True
+        self.rebalance_every, self.rebalance_threshold = int(rebalance_every), float(rebalance_threshold)
+        self.cap_factor = cap_factor if cap_factor is not None else (1.30 if rebalance_every else 1.15)
+        self.steps_done = 0
+        self.last_rebalance_at = 0
+        self.n_rebalances = 0
 
     def _ck(self, rc):
         if rc != api.PBF_OK:
@@ -195,12 +227,33 @@ class SlabSolver:
             per_col = max(int(hist.max()), 1)           # global, so message sizes agree on both ends
             self.halo_cap = int(max(4096, self.halo_factor * per_col))
             owned_est = int(hist[lo:hi].sum())
-            self.particle_cap = int(max(n, owned_est) * 1.15 + 2 * self.halo_cap + 1024)
-            self._ck(self.lib.pbf_slab_configure(self.h, lo, hi, left_cols, right_cols, self.particle_cap, self.halo_cap))
+            mean_owned = int(hist.sum()) // self.world + 1
+            self.particle_cap = int(max(n, owned_est, mean_owned) * self.cap_factor + 2 * self.halo_cap + 1024)
+            ncol = self.gdims[0]
+            cells_per_col = self.gdims[1] * self.gdims[2]
+            max_cols = ncol if cells_per_col * ncol * 8.0 <= 2e9 else min(ncol, 4 * (hi - lo) + 16)
+            self._ck(self.lib.pbf_slab_configure_ex(self.h, lo, hi, left_cols, right_cols, self.particle_cap, self.halo_cap, max_cols))
             self._map_buffers()
+            if self.transport == "p2p":
+                self._connect_p2p()
             self.bounds = (0, 0, 0, 0, 0)
         self._ck(self.lib.pbf_slab_upload(self.h, n, pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p)))
         self.solver.n = n
+
+    def _connect_p2p(self):
+        """Exchange CUDA IPC handles of the buffers the x-neighbours write into; from here on the step needs no transport."""
+        dist = self.dist
+        nb = self.lib.pbf_slab_p2p_blob_size()
+        blob = C.create_string_buffer(nb)
+        self._ck(self.lib.pbf_slab_p2p_export(self.h, blob))
+        blobs = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(blobs, blob.raw)
+        left = C.create_string_buffer(blobs[self.left], nb) if self.left is not None else None
+        right = C.create_string_buffer(blobs[self.right], nb) if self.right is not None else None
+        self._ck(self.lib.pbf_slab_p2p_connect_ipc(self.h, left, right))
+        if self.world > 1:
+            dist.barrier()        # nobody steps before every neighbour is mapped
 
     def _map_buffers(self):
         torch = self.torch
@@ -219,8 +272,45 @@ class SlabSolver:
         exchange(self.dist, [("send", a[b0:b1], self.left), ("recv", a[0:b0], self.left),
                              ("send", a[b2:b3], self.right), ("recv", a[b3:n], self.right)], staged=self.staged)
 
+    def _rebalance(self):
+        """Between two steps: move the slab boundaries towards equal counts when the fluid has flowed (every rank takes
+        the same decision from the same all-reduced histogram; the next predict pass migrates the particles)."""
+        torch, dist, lib = self.torch, self.dist, self.lib
+        if self.world < 2 or not self.rebalance_every or self.steps_done == 0 or self.steps_done % self.rebalance_every:
+            return
+        ncol = self.gdims[0]
+        hist = np.zeros(ncol, dtype=np.uint32); at = C.c_longlong(-1)
+        rc = lib.pbf_slab_column_histogram(self.h, hist.ctypes.data_as(C.c_void_p), ncol, 1, C.byref(at))
+        lo, hi = self.col_bounds[self.rank], self.col_bounds[self.rank + 1]
+        own = np.zeros(ncol + 1, dtype=np.int64); own[lo:hi] = hist[lo:hi]
+        own[ncol] = 1 if rc == api.PBF_OK and at.value >= self.last_rebalance_at else 0     # taken under the current plan? (the all-reduce below is collective either way)
+        t = torch.from_numpy(own)
+        t = t.to(f"cuda:{self.device}") if dist.get_backend() == "nccl" else t
+        dist.all_reduce(t)
+        own = t.cpu().numpy()
+        if own[ncol] != self.world:
+            return
+        g = np.ascontiguousarray(own[:ncol], dtype=np.uint64)
+        old = np.ascontiguousarray(self.col_bounds, dtype=np.int32); new = np.zeros_like(old); imb = C.c_double()
+        ch = lib.pbf_plan_rebalance(g.ctypes.data_as(C.c_void_p), ncol, self.world, old.ctypes.data_as(C.c_void_p), int(0.4 * self.halo_cap),
+                                    self.rebalance_threshold, new.ctypes.data_as(C.c_void_p), C.byref(imb))
+        self.imbalance = imb.value
+        if ch != 1:
+            return
+        b = [int(v) for v in new]
+        r = self.rank
+        self._ck(lib.pbf_slab_set_columns(self.h, b[r], b[r + 1], b[r] - b[r - 1] if r > 0 else 0, b[r + 2] - b[r + 1] if r + 1 < self.world else 0))
+        self.col_bounds = b
+        self.last_rebalance_at = self.steps_done
+        self.n_rebalances += 1
+
     def _step_once(self):
         lib, h, B = self.lib, self.h, self.buf
+        self._rebalance()
+        self.steps_done += 1
+        if self.transport == "p2p":
+            self._ck(lib.pbf_slab_step_p2p(h, 1))
+            return
         self._ck(lib.pbf_slab_phase_predict(h))
         exchange(self.dist, [("send", B[BUF_MIG_SEND_L], self.left), ("recv", B[BUF_MIG_RECV_L], self.left),
                              ("send", B[BUF_MIG_SEND_R], self.right), ("recv", B[BUF_MIG_RECV_R], self.right)], staged=self.staged)
@@ -273,6 +363,10 @@ class SlabSolver:
     def sync(self):
         self.stream.synchronize()
         self.solver.sync()
+        if self.transport == "p2p" and self.bounds is not None:
+            out = (C.c_uint32 * 5)()
+            self._ck(self.lib.pbf_slab_refresh_ranges(self.h, C.byref(out)))     # the ranges stayed on the device during the step
+            self.bounds = tuple(int(v) for v in out)
         if getattr(self, "_timed", False):
             self._last_ms = self._ev[0].elapsed_time(self._ev[1]); self._timed = False
 

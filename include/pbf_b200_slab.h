@@ -47,6 +47,43 @@ int pbf_set_stream(pbf_handle* h, void* cuda_stream);
  * particles; halo_cap bounds each migration / ghost message (particles).  Call before uploading. */
 int pbf_slab_configure(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int right_cols,
                        size_t particle_cap, size_t halo_cap);
+/* Same, with room for re-balancing: the cell arrays are sized for max_cols owned columns (0 = gx_hi - gx_lo), so
+ * pbf_slab_set_columns may later move the slab's boundaries within that width. */
+int pbf_slab_configure_ex(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int right_cols,
+                          size_t particle_cap, size_t halo_cap, int max_cols);
+/* Re-balancing ("re-balanced only when imbalance > few %"): change the owned columns between two steps.
+ * Every rank must be given consistent ranges.  Nothing moves here: the next predict pass finds every particle whose
+ * column changed hands outside [gx_lo, gx_hi) and sends it through the ordinary migration message, so a boundary may
+ * move by at most as many columns as one message holds (halo_cap particles) and only to the adjacent slab. */
+int pbf_slab_set_columns(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int right_cols);
+int pbf_slab_columns(pbf_handle* h, int gx_lo_hi_left_right_out[4]);
+/* Owned particles per GLOBAL cell column (n_cols = pbf_grid_dims()[0]) after the sort of a recent step.  The sort phase
+ * enqueues the copy whenever the previous one has been delivered, so with wait = 0 this never stalls the pipeline
+ * (PBF_ERR_INVALID while a copy is in flight); wait = 1 blocks until the pending copy has arrived.  *step_out = how many
+ * steps the handle had completed before the step whose sort the histogram describes. */
+int pbf_slab_column_histogram(pbf_handle* h, uint32_t* hist_out, size_t n_cols, int wait, long long* step_out);
+
+/* ---- peer mode: the exchanges inside the library, over peer-mapped memory -------------------------------------------
+ * After pbf_slab_p2p_connect_* a slab handle writes its migration / ghost messages and, from inside the solver kernels,
+ * the per-iteration boundary values DIRECTLY into its x-neighbours' device memory (NVLink peer stores), learns the
+ * neighbours' ranges from their device-resident link block, and hands over with flag words instead of host
+ * synchronisation: pbf_slab_step_p2p enqueues whole steps with no host round trip, no copy-engine work and no
+ * communication library.  Every rank must enqueue the same number of steps.  Results are bit-identical to the
+ * host-driven protocol and to one GPU.
+ *   same process (pbf_create_multi):   pbf_slab_p2p_connect_local(h, left_handle, right_handle)
+ *   one process per GPU:               pbf_slab_p2p_export(h, blob) on every rank, exchange the blobs (any transport),
+ *                                      pbf_slab_p2p_connect_ipc(h, left_blob, right_blob)            (CUDA IPC)
+ * NULL = no neighbour on that side.  A neighbour that never arrives at an exchange point makes the waiting rank give up
+ * after pbf_slab_set_wait_timeout seconds (default 20) with an error at the next pbf_sync, never a hang. */
+int pbf_slab_p2p_connect_local(pbf_handle* h, pbf_handle* left, pbf_handle* right);
+size_t pbf_slab_p2p_blob_size(void);
+int pbf_slab_p2p_export(pbf_handle* h, void* blob_out);
+int pbf_slab_p2p_connect_ipc(pbf_handle* h, const void* left_blob, const void* right_blob);
+int pbf_slab_set_wait_timeout(pbf_handle* h, double seconds);
+int pbf_slab_step_p2p(pbf_handle* h, int n_steps);                    /* asynchronous */
+/* Synchronises and returns b0, b1, b2, b3, n of the last sort (peer mode keeps them on the device during the step). */
+int pbf_slab_refresh_ranges(pbf_handle* h, uint32_t bounds_out[5]);
+
 /* Owned particles of this rank with their GLOBAL ids (host, fp64 AoS). */
 int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double* vel_xyz, const uint32_t* ids);
 /* Owned particles, in the rank's current sorted order (fp64 AoS) + ids; *n_out = count. */

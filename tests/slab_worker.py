@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--same-gpu", action="store_true")
     ap.add_argument("--spheres", action="store_true", help="obstacle spheres on the floor, one of them across a slab boundary")
     ap.add_argument("--mesh", action="store_true", help="a tessellated sphere (device BVH) across the slab boundary")
+    ap.add_argument("--transport", default=None, help="p2p (CUDA IPC, the library's peer mode) | nccl | staged; default: SlabSolver's choice")
+    ap.add_argument("--flow", action="store_true", help="shallow block pushed along x in a long tank: the slabs have to be re-balanced")
+    ap.add_argument("--rebalance-every", type=int, default=8)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -51,6 +54,11 @@ def main():
     box_max = (0.1 * nx + 0.4, 0.1 * ny + 2.0, 0.1 * nz + 0.3)
     prm = dict(rest_density=700.0, iterations=args.iterations, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
     pos, vel = scene(nx, ny, nz)
+    if args.flow:
+        from helpers import lattice_block
+        pos, vel = lattice_block(nx, ny, nz, origin=(0.1, 0.1, 0.1), spacing=0.1, v0=(3.0, -1.0, 0.0), jitter=0.001, seed=5)
+        box_max = (0.3 * nx + 0.3, 4.0, 0.1 * nz + 0.3)
+        prm.update(box_max=box_max, y_light=box_max[1], z_front=box_max[2])
     # obstacle spheres are global scene data: every rank sets the same list.  The first one sits on the slab
     # boundary of a 2-rank run; particles that would start inside a sphere are left out of the block.
     spheres = np.array([[0.05 * nx, 0.6, 0.05 * nz, 0.7], [0.025 * nx, 1.2, 0.03 * nz, 0.5]]) if args.spheres else np.zeros((0, 4))
@@ -68,7 +76,7 @@ def main():
     # rank r starts with the r-th contiguous chunk of the x-outer lattice order (roughly its slab)
     per = n // world
     lo = rank * per; hi = n if rank == world - 1 else (rank + 1) * per
-    s = slab.SlabSolver(api.default_params(**prm), rank, world, device=local)
+    s = slab.SlabSolver(api.default_params(**prm), rank, world, device=local, transport=args.transport, rebalance_every=args.rebalance_every)
     s.set_obstacle_spheres(spheres)
     if mesh is not None:
         s.set_obstacle_triangles(mesh)
@@ -76,7 +84,13 @@ def main():
     s.step(args.steps); s.sync()
     P, V, R, I, d, c = s.gather_all()
     a_first, a_final = s.stats()
-    out = {"world": world, "n": int(n), "steps": args.steps, "bounds": list(s.bounds), "col_bounds": list(map(int, s.col_bounds))}
+    owned = [0] * world
+    if world > 1:
+        dist.all_gather_object(owned, int(s.n_owned()))
+    else:
+        owned = [int(s.n_owned())]
+    out = {"world": world, "n": int(n), "steps": args.steps, "bounds": list(s.bounds), "col_bounds": list(map(int, s.col_bounds)),
+           "transport": s.transport, "n_rebalances": s.n_rebalances, "owned": owned}
     if rank == 0:
         g = api.Solver(api.default_params(**prm), device=local)
         g.set_obstacle_spheres(spheres)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     syms = set()
-    for hdr in ("pbf_b200.h", "pbf_b200_slab.h"):
+    for hdr in ("pbf_b200.h", "pbf_b200_slab.h", "pbf_b200_multi.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         syms |= set(re.findall(r"\b(pbf_[a-z0-9_]+)\s*\(", text))
@@ -225,3 +225,47 @@ def test_hierarchy_walk_equals_scan_in_a_model_of_the_device_code():
         hits += b1 >= 0; contacts += (b1 >= 0 and t1 == 0.0); visited_total += vis
     assert hits > trials // 4 and contacts > 20
     assert visited_total < 0.1 * trials * n                                   # and the walk does prune
+
+
+def test_slab_planners_on_host():
+    """pbf_partition_columns / pbf_plan_rebalance (pure host, fluid_b200/csrc/pbf_multi.cpp): the planner of pbf_create_multi
+    equals slab.partition_columns, and a re-balancing move keeps every boundary strictly between its old neighbours (one
+    migration hop), moves towards the equal-count partition and never carries more than the message budget."""
+    from fluid_b200 import api, slab
+    lib = api.load_library()
+    lib.pbf_partition_columns.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.pbf_plan_rebalance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        ncol = int(rng.integers(1, 60)); world = int(rng.integers(1, min(ncol, 8) + 1))
+        hist = rng.integers(0, 1000, size=ncol).astype(np.uint64)
+        if trial % 5 == 0:
+            hist[rng.integers(0, ncol):] = 0             # fluid only in a part of the tank
+        out = np.zeros(world + 1, dtype=np.int32)
+        assert lib.pbf_partition_columns(hist.ctypes.data, ncol, world, out.ctypes.data) == 0
+        assert list(out) == slab.partition_columns(hist, world)
+    # a dam break: all the fluid in the left third at first, then spread evenly; the slabs follow step by step
+    ncol, world = 90, 4
+    hist0 = np.zeros(ncol, dtype=np.uint64); hist0[:30] = 1000
+    b = np.zeros(world + 1, dtype=np.int32); lib.pbf_partition_columns(hist0.ctypes.data, ncol, world, b.ctypes.data)
+    assert list(b) == [0, 8, 15, 22, 90] or b[-1] == 90
+    hist1 = np.full(ncol, 333, dtype=np.uint64)
+    imb = C.c_double()
+    for it in range(200):
+        owned_hist = hist1.copy()
+        nb = np.zeros(world + 1, dtype=np.int32)
+        ch = lib.pbf_plan_rebalance(owned_hist.ctypes.data, ncol, world, b.ctypes.data, 1500, 1.05, nb.ctypes.data, C.byref(imb))
+        assert ch in (0, 1)
+        assert nb[0] == 0 and nb[-1] == ncol and np.all(np.diff(nb) >= 1)
+        for k in range(1, world):
+            assert b[k - 1] < nb[k] < b[k + 1]                                     # one hop
+            lo, hi = sorted((int(b[k]), int(nb[k])))
+            assert owned_hist[lo:hi].sum() <= 1500                                  # fits the message budget
+        if ch == 0:
+            break
+        b = nb
+    owned = np.array([hist1[b[r]:b[r + 1]].sum() for r in range(world)], dtype=np.float64)
+    assert owned.max() / owned.mean() <= 1.05 and it < 60, (list(b), it)
+    # balanced input: nothing moves
+    nb = np.zeros(world + 1, dtype=np.int32)
+    assert lib.pbf_plan_rebalance(hist1.ctypes.data, ncol, world, b.ctypes.data, 1500, 1.05, nb.ctypes.data, C.byref(imb)) == 0 and list(nb) == list(b)
