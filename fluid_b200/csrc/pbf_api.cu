@@ -159,11 +159,14 @@ int check_device_errors(pbf_handle* h) {
     int zero = 0;
     cudaMemcpy(&h->sc->err, &zero, sizeof(int), cudaMemcpyHostToDevice);
     if (s.err & ERRBIT_NONFINITE) return fail(h, PBF_ERR_DOMAIN, "non-finite particle position produced by the step");
+    if (s.err & ERRBIT_PEER_TIMEOUT) {
+      const std::string who = s.timeout_missing == 3 ? "both neighbours" : (s.timeout_missing == 1 ? "the left neighbour" : "the right neighbour");
+      return fail(h, PBF_ERR_CUDA, ("peer mode: " + who + " did not reach exchange point " + std::to_string(s.timeout_epoch) + " in time").c_str());
+    }
     if (s.err & ERRBIT_MIGRATION) return fail(h, PBF_ERR_DOMAIN, "particle left its slab by more than one cell column in one step");
     if (s.err & ERRBIT_NBR_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "neighbour list capacity exceeded (raise PBF_NBR_ROWS); results of this step are invalid");
     if (s.err & ERRBIT_HALO_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "halo / migration buffer capacity exceeded");
     if (s.err & ERRBIT_SLAB_CAPACITY) return fail(h, PBF_ERR_CAPACITY, "slab particle capacity exceeded (owned + ghost particles > particle_cap)");
-    if (s.err & ERRBIT_PEER_TIMEOUT) return fail(h, PBF_ERR_CUDA, "peer mode: a neighbouring slab did not reach the exchange point in time");
     if (s.err & ERRBIT_PEER_MISMATCH) return fail(h, PBF_ERR_DOMAIN, "peer mode: boundary column and the neighbour's ghost range differ in length");
     return fail(h, PBF_ERR_CUDA, "unknown device error flag");
   }
@@ -272,7 +275,7 @@ void pbf_destroy(pbf_handle* h) {
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   for (int k = 0; k < 2; k++) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); cudaFree(h->ghost_send[k]); cudaFree(h->ghost_recv[k]); }
   for (int k = 0; k < 2; k++) if (h->peer[k].ipc) for (void* p : h->peer[k].ipc_base) if (p) cudaIpcCloseMemHandle(p);
-  cudaFree(h->link); cudaFree(h->col_hist);
+  cudaFree(h->link);
   if (h->col_hist_host) cudaFreeHost(h->col_hist_host);
   if (h->ev_hist) cudaEventDestroy(h->ev_hist);
   delete static_cast<HandleExtra*>(h->host_extra);

@@ -37,6 +37,7 @@ struct Scalars {
   unsigned int alert_count;        // particles below the neighbour-count alert threshold in the last step
   unsigned int alert_kept;         // ... of which this many have a record (ids below alert_bound)
   unsigned int alert_bound, pad2;
+  unsigned int timeout_epoch, timeout_missing;   // peer mode: the exchange point that gave up, and who was missing (1 left, 2 right)
 };
 
 enum KernelId { K_PREDICT = 0, K_SCAN, K_SCATTER, K_CELLSORT, K_REORDER, K_NEIGHBORS, K_LAMBDA, K_DELTA,
@@ -90,9 +91,9 @@ struct Solver {
   } peer[2];                         // [0] left, [1] right
   uint32_t epoch = 0;                // signals issued so far (identical sequence on every rank)
   long long wait_timeout_ns = 20000000000ll;
-  uint32_t* col_hist = nullptr;      // owned particles per global cell column after the last sort (re-balancing), device
-  uint32_t* col_hist_host = nullptr; // ... its pinned host copy
+  uint32_t* col_hist_host = nullptr; // owned particles per global cell column after a sort (re-balancing): page-locked host memory the kernel stores into
   cudaEvent_t ev_hist = nullptr;
+  int hist_every = 0;                // > 0: record the histogram at the sorts of steps that are multiples of it; 0: whenever the last one was delivered
   long long hist_step = -1;          // step index (steps_done at its sort) of the histogram in flight / delivered
   Scalars* sc = nullptr;             // device
   float* io_stage = nullptr;         // device staging for original-order fp32 AoS (7 floats / particle)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,6 +87,8 @@ struct pbf_multi {
   int rebalance_every = 8; double rebalance_threshold = 1.05;
   long long steps_done = 0, last_rebalance_at = 0; uint64_t n_rebalances = 0;
   std::vector<uint32_t> hist_tmp; std::vector<uint64_t> hist;
+  double last_imbalance = 1.0;
+  bool trace = getenv("PBF_MULTI_TRACE") != nullptr;
 };
 
 namespace {
@@ -116,21 +119,29 @@ int apply_scene(pbf_multi* m) {
   return PBF_OK;
 }
 
-// move the boundaries if the slabs have drifted apart (called between two steps; never waits for a device)
+// Move the boundaries if the slabs have drifted apart (called between two steps).  The histograms are those the sorts of
+// step (steps_done - every) left behind: this thread waits for them, i.e. it runs at most `every` steps ahead of the devices,
+// which still have the steps enqueued since then to work on.  The schedule is a function of the step count only.
 void maybe_rebalance(pbf_multi* m) {
   const int world = (int)m->h.size(), ncol = m->gdims[0];
   if (world < 2 || m->rebalance_every <= 0 || m->steps_done == 0 || m->steps_done % m->rebalance_every != 0) return;
   m->hist.assign(ncol, 0); m->hist_tmp.resize(ncol);
   for (int d = 0; d < world; d++) {
     long long at = -1;
-    if (pbf_slab_column_histogram(m->h[d], m->hist_tmp.data(), (size_t)ncol, 0, &at) != PBF_OK) return;    // still in flight: next time
-    if (at < m->last_rebalance_at) return;               // taken under an older plan: the budget below needs true counts
+    if (pbf_slab_column_histogram(m->h[d], m->hist_tmp.data(), (size_t)ncol, 1, &at) != PBF_OK) return;
+    if (at != m->steps_done - m->rebalance_every || at < m->last_rebalance_at) return;   // not the one expected (interval just changed) or taken under an older plan
     for (int c = m->col_bounds[d]; c < m->col_bounds[d + 1]; c++) m->hist[c] = m->hist_tmp[c];
   }
   std::vector<int> nb(world + 1);
   double imb = 1.0;
   const int changed = pbf_plan_rebalance(m->hist.data(), ncol, world, m->col_bounds.data(), (uint64_t)(0.4 * (double)m->halo_cap),
                                          m->rebalance_threshold, nb.data(), &imb);
+  if (m->trace) {
+    fprintf(stderr, "[pbf_multi] step %lld imbalance %.4f changed %d bounds", m->steps_done, imb, changed);
+    for (int k = 0; k <= world; k++) fprintf(stderr, " %d->%d", m->col_bounds[k], nb[k]);
+    fprintf(stderr, "\n");
+  }
+  m->last_imbalance = imb;
   if (changed != 1) return;
   for (int d = 0; d < world; d++) {
     const int left = d > 0 ? nb[d] - nb[d - 1] : 0, right = d + 1 < world ? nb[d + 2] - nb[d + 1] : 0;
@@ -196,6 +207,7 @@ int pbf_multi_set_obstacle_triangles(pbf_multi* m, size_t count, const double* t
 int pbf_multi_set_rebalance(pbf_multi* m, int every_k_steps, double threshold) {
   if (!m || every_k_steps < 0 || !(threshold >= 1.0)) return PBF_ERR_INVALID;
   m->rebalance_every = every_k_steps; m->rebalance_threshold = threshold;
+  if (m->planned) for (pbf_handle* q : m->h) pbf_slab_set_histogram_interval(q, every_k_steps);
   return PBF_OK;
 }
 
@@ -235,6 +247,7 @@ int pbf_multi_upload(pbf_multi* m, size_t n, const double* pos_xyz, const double
     rc = pbf_slab_configure_ex(m->h[r], m->col_bounds[r], m->col_bounds[r + 1], left, right, m->particle_cap, m->halo_cap, max_cols);
     if (rc != PBF_OK) return from_handle(m, r, rc);
   }
+  for (int r = 0; r < world; r++) pbf_slab_set_histogram_interval(m->h[r], m->rebalance_every);
   for (int r = 0; r < world; r++) {
     rc = pbf_slab_p2p_connect_local(m->h[r], r > 0 ? m->h[r - 1] : nullptr, r + 1 < world ? m->h[r + 1] : nullptr);
     if (rc != PBF_OK) return from_handle(m, r, rc);
@@ -276,11 +289,14 @@ int pbf_multi_step(pbf_multi* m, int n_steps) {
 
 int pbf_multi_sync(pbf_multi* m) {
   if (!m) return PBF_ERR_INVALID;
-  int first = PBF_OK;
-  for (size_t d = 0; d < m->h.size(); d++) {             // wait for ALL devices even after an error
+  int first = PBF_OK; std::string all;
+  for (size_t d = 0; d < m->h.size(); d++) {             // wait for ALL devices even after an error, and report every one of them
     int rc = pbf_sync(m->h[d]);
-    if (rc != PBF_OK && first == PBF_OK) first = from_handle(m, (int)d, rc);
+    if (rc == PBF_OK) continue;
+    if (first == PBF_OK) first = rc;
+    all += (all.empty() ? "" : "; ") + std::string("slab ") + std::to_string(d) + " (device " + std::to_string(m->devices[d]) + "): " + pbf_last_error(m->h[d]);
   }
+  if (first != PBF_OK) m->last_error = all;
   return first;
 }
 

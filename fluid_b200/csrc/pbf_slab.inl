@@ -110,6 +110,7 @@ k_column_hist(const uint32_t* __restrict__ cell_start, uint32_t gyz, int gx_lo, 
   if (c >= n_global_cols) return;
   const int local = c - gx_lo;                                    // owned columns are local columns 1 .. n_owned_cols
   hist[c] = (local >= 0 && local < n_owned_cols) ? cell_start[(uint32_t)(local + 2) * gyz] - cell_start[(uint32_t)(local + 1) * gyz] : 0u;
+  __threadfence_system();                                         // hist is page-locked host memory
 }
 
 // ---- peer mode: flags and ranges through peer-mapped memory ---------------------------------------------------------
@@ -133,7 +134,7 @@ __global__ void k_wait(const uint32_t* flag_left, const uint32_t* flag_right, ui
     const bool r = !flag_right || (int)(*reinterpret_cast<const volatile uint32_t*>(flag_right) - epoch) >= 0;
     if (l && r) break;
     unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if ((long long)(t1 - t0) > timeout_ns) { atomicOr(&sc->err, ERRBIT_PEER_TIMEOUT); break; }
+    if ((long long)(t1 - t0) > timeout_ns) { sc->timeout_epoch = epoch; sc->timeout_missing = (l ? 0u : 1u) | (r ? 0u : 2u); atomicOr(&sc->err, ERRBIT_PEER_TIMEOUT); break; }
     __nanosleep(200);
   }
   __threadfence_system();
@@ -260,9 +261,7 @@ int pbf_slab_configure_ex(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, in
   }
   SCK(h, cudaMalloc((void**)&h->link, sizeof(SlabLink)));
   SCK(h, cudaMemset(h->link, 0, sizeof(SlabLink)));
-  SCK(h, cudaMalloc((void**)&h->col_hist, (size_t)h->dp.gdim_x_global * 4));
-  SCK(h, cudaMemset(h->col_hist, 0, (size_t)h->dp.gdim_x_global * 4));
-  SCK(h, cudaMallocHost((void**)&h->col_hist_host, (size_t)h->dp.gdim_x_global * 4));
+  SCK(h, cudaHostAlloc((void**)&h->col_hist_host, (size_t)h->dp.gdim_x_global * 4, cudaHostAllocPortable | cudaHostAllocMapped));
   std::memset(h->col_hist_host, 0, (size_t)h->dp.gdim_x_global * 4);
   SCK(h, cudaEventCreateWithFlags(&h->ev_hist, cudaEventDisableTiming));
   return PBF_OK;
@@ -272,6 +271,12 @@ int pbf_slab_set_columns(pbf_handle* h, int gx_lo, int gx_hi, int left_cols, int
   if (!h || !h->slab) return PBF_ERR_INVALID;
   // kernels in flight hold the old grid in their parameters (by value), so changing it for LATER launches needs no sync
   return apply_columns(h, gx_lo, gx_hi, left_cols, right_cols);
+}
+
+int pbf_slab_set_histogram_interval(pbf_handle* h, int every_k_steps) {
+  if (!h || !h->slab || every_k_steps < 0) return PBF_ERR_INVALID;
+  h->hist_every = every_k_steps;
+  return PBF_OK;
 }
 
 int pbf_slab_columns(pbf_handle* h, int out[4]) {
@@ -369,9 +374,13 @@ static int enqueue_slab_sort(pbf_handle* h) {
   h->prof_begin(K_SLAB);
   k_gather_bounds<<<1, 32, 0, h->stream>>>(h->cell_start, gyz, 2 * gyz, m * gyz, (m + 1) * gyz, h->ncell, h->sc, h->link, (uint32_t)h->append_base);
   h->prof_end(K_SLAB); h->launches++;
-  if (cudaEventQuery(h->ev_hist) == cudaSuccess) {       // the previous histogram has been delivered: record the next one
-    LAUNCH(h, K_SLAB, k_column_hist, blocks_for(h->dp.gdim_x_global), h->cell_start, gyz, h->dp.gx_lo, (int)m, h->dp.gdim_x_global, h->col_hist);
-    cudaMemcpyAsync(h->col_hist_host, h->col_hist, (size_t)h->dp.gdim_x_global * 4, cudaMemcpyDeviceToHost, h->stream);
+  // hist_every > 0 (pbf_slab_set_histogram_interval, what pbf_multi uses): on the steps the driver names, which makes the
+  // re-balancing a pure function of the step count; otherwise whenever the previous histogram has been delivered
+  const bool record = h->hist_every > 0 ? (h->steps_done % (uint64_t)h->hist_every == 0) : (cudaEventQuery(h->ev_hist) == cudaSuccess);
+  if (record) {
+    // stored straight into page-locked host memory by the kernel: a copy-engine transfer here would queue behind the other
+    // slabs' copies when several slabs share a GPU, and a slab waiting at an exchange point would then block its neighbour
+    LAUNCH(h, K_SLAB, k_column_hist, blocks_for(h->dp.gdim_x_global), h->cell_start, gyz, h->dp.gx_lo, (int)m, h->dp.gdim_x_global, h->col_hist_host);
     cudaEventRecord(h->ev_hist, h->stream);
     h->hist_step = (long long)h->steps_done;             // the step whose sort it describes
   } else cudaGetLastError();
@@ -465,6 +474,26 @@ int pbf_slab_refresh_ranges(pbf_handle* h, uint32_t bounds_out[5]) {
   return PBF_OK;
 }
 
+}  // extern "C"
+
+// CUDA loads a kernel's code at its first launch, and that load may have to wait until the device is idle: a rank that
+// sits in k_wait for a neighbour whose launches the (blocked) host thread has not issued yet would never be released.
+// Everything a peer-mode step launches is therefore loaded before the first step (cudaFuncGetAttributes loads a function).
+static void preload_step_kernels() {
+  cudaFuncAttributes a;
+#define PL(...) cudaFuncGetAttributes(&a, __VA_ARGS__)
+  PL(k_predict_hash<true>); PL(k_predict_hash<false>); PL(k_scan_reduce); PL(k_scan_block_sums); PL(k_scan_apply); PL(k_scatter);
+  PL(k_cell_sort); PL(k_reorder); PL(k_build_neighbors); PL(k_alert_hist); PL(k_alert_bound); PL(k_neighbor_alert); PL(k_set_sentinel);
+  PL(k_lambda); PL(k_delta<4, true>); PL(k_delta<4, false>); PL(k_delta<-1, true>); PL(k_delta<-1, false>); PL(k_velocity);
+  PL(k_vorticity_xsph); PL(k_confine_commit); PL(k_write_headers); PL(k_absorb_migrants); PL(k_pack_ghosts); PL(k_absorb_ghosts);
+  PL(k_gather_bounds); PL(k_column_hist); PL(k_signal); PL(k_wait); PL(k_fetch_peer_ranges); PL(k_neighbor_digest);
+  PL(k_export3_f64); PL(k_export1_f64); PL(k_export3); PL(k_export1); PL(k_export_w);
+#undef PL
+  cudaGetLastError();
+}
+
+extern "C" {
+
 // Connect to the x-neighbours' memory.  Same process: the handles themselves (peer access is enabled here).
 int pbf_slab_p2p_connect_local(pbf_handle* h, pbf_handle* left, pbf_handle* right) {
   if (!h || !h->slab || !h->link) return sfail(h, PBF_ERR_INVALID, "pbf_slab_p2p_connect_local: configure the slab first");
@@ -488,6 +517,7 @@ int pbf_slab_p2p_connect_local(pbf_handle* h, pbf_handle* left, pbf_handle* righ
     P.mig_recv = q->mig_recv[s ^ 1]; P.ghost_recv = q->ghost_recv[s ^ 1];      // we are on the OTHER side of the neighbour
     P.ipc = false;
   }
+  preload_step_kernels();
   h->p2p = true;
   return PBF_OK;
 }
@@ -522,6 +552,7 @@ int pbf_slab_p2p_connect_ipc(pbf_handle* h, const void* left_blob, const void* r
     P.mig_recv = (float4*)got[4]; P.ghost_recv = (float4*)got[5];
     P.ipc = true;
   }
+  preload_step_kernels();
   h->p2p = true;
   return PBF_OK;
 }

@@ -62,6 +62,10 @@ int pbf_slab_columns(pbf_handle* h, int gx_lo_hi_left_right_out[4]);
  * (PBF_ERR_INVALID while a copy is in flight); wait = 1 blocks until the pending copy has arrived.  *step_out = how many
  * steps the handle had completed before the step whose sort the histogram describes. */
 int pbf_slab_column_histogram(pbf_handle* h, uint32_t* hist_out, size_t n_cols, int wait, long long* step_out);
+/* every_k_steps > 0: record the histogram at the sorts of steps 0, k, 2k, ... instead (the caller reads each one, with
+ * wait = 1, before it enqueues the step that records the next): the schedule of a re-balancing driver then depends on
+ * the step count only, not on how far the host runs ahead of the devices.  0 restores the default above. */
+int pbf_slab_set_histogram_interval(pbf_handle* h, int every_k_steps);
 
 /* ---- peer mode: the exchanges inside the library, over peer-mapped memory -------------------------------------------
  * After pbf_slab_p2p_connect_* a slab handle writes its migration / ghost messages and, from inside the solver kernels,
