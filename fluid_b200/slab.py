@@ -47,6 +47,7 @@ def _bind(lib):
         "pbf_slab_p2p_connect_ipc": (i32, [vp, vp, vp]),
         "pbf_slab_set_wait_timeout": (i32, [vp, C.c_double]),
         "pbf_slab_step_p2p": (i32, [vp, i32]),
+        "pbf_slab_set_histogram_interval": (i32, [vp, i32]),
         "pbf_slab_refresh_ranges": (i32, [vp, C.POINTER(C.c_uint32 * 5)]),
         "pbf_partition_columns": (i32, [vp, i32, i32, vp]),
         "pbf_plan_rebalance": (i32, [vp, i32, i32, vp, C.c_uint64, C.c_double, vp, C.POINTER(C.c_double)]),
@@ -234,6 +235,8 @@ class SlabSolver:
             max_cols = ncol if cells_per_col * ncol * 8.0 <= 2e9 else min(ncol, 4 * (hi - lo) + 16)
             self._ck(self.lib.pbf_slab_configure_ex(self.h, lo, hi, left_cols, right_cols, self.particle_cap, self.halo_cap, max_cols))
             self._map_buffers()
+            if self.rebalance_every:
+                self._ck(self.lib.pbf_slab_set_histogram_interval(self.h, self.rebalance_every))   # recorded on named steps: a deterministic schedule
             if self.transport == "p2p":
                 self._connect_p2p()
             self.bounds = (0, 0, 0, 0, 0)
