@@ -781,7 +781,8 @@ k_xsph_reference(const __grid_constant__ DevParams P, uint32_t n, const float4* 
 __global__ void __launch_bounds__(TPB)
 k_density_only(const __grid_constant__ DevParams P, uint32_t i0, uint32_t n, const float4* __restrict__ xs,
                float* __restrict__ rho_out, const uint32_t* __restrict__ nbr,
-               const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt) {
+               const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt, const SlabLink* __restrict__ lk) {
+  if (lk) { i0 = lk->b[0]; n = lk->b[3] - lk->b[0]; }
   const uint32_t t = blockIdx.x * TPB + threadIdx.x;
   const uint32_t i = i0 + t;
   if (t >= n) return;
@@ -1125,7 +1126,7 @@ void enqueue_estimate_densities(Solver* h) {
   enqueue_predict_hash(h, 0);
   enqueue_sort(h, n);
   enqueue_build(h, 1);
-  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, 0u, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt);
+  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(n), h->dp, 0u, n, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt, (const SlabLink*)nullptr);
 }
 
 // re-bin the particles by their COMMITTED positions (after a step the cells are those of the predicted

@@ -287,6 +287,16 @@ int pbf_multi_step(pbf_multi* m, int n_steps) {
   return PBF_OK;
 }
 
+int pbf_multi_estimate_densities(pbf_multi* m) {
+  if (!m) return PBF_ERR_INVALID;
+  if (!m->planned) return mfail(m, PBF_ERR_INVALID, "pbf_multi_estimate_densities: upload particles first");
+  for (size_t d = 0; d < m->h.size(); d++) {
+    int rc = pbf_slab_estimate_densities_p2p(m->h[d]);
+    if (rc != PBF_OK) return from_handle(m, (int)d, rc);
+  }
+  return PBF_OK;
+}
+
 int pbf_multi_sync(pbf_multi* m) {
   if (!m) return PBF_ERR_INVALID;
   int first = PBF_OK; std::string all;

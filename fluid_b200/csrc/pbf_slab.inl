@@ -323,12 +323,12 @@ int pbf_slab_upload(pbf_handle* h, size_t n, const double* pos_xyz, const double
   return PBF_OK;
 }
 
-// A. predict owned particles; emigrants go to the migration messages
-int pbf_slab_phase_predict(pbf_handle* h) {
+// A. predict owned particles (apply_forces = 0: only re-bin the committed positions); emigrants go to the migration messages
+static int slab_predict(pbf_handle* h, int apply_forces) {
   if (!h || !h->slab) return PBF_ERR_INVALID;
   SCK(h, cudaSetDevice(h->device));
   cudaMemsetAsync(&h->sc->rho_first, 0, 2 * sizeof(double), h->stream);
-  enqueue_predict_hash(h, 1);
+  enqueue_predict_hash(h, apply_forces);
   h->prof_begin(K_SLAB);
   k_write_headers<<<1, 32, 0, h->stream>>>(h->sc, h->has_left ? mig_out(h, 0) : nullptr, h->has_right ? mig_out(h, 1) : nullptr,
                                            nullptr, nullptr, (uint32_t)h->halo_cap, 0);
@@ -336,6 +336,8 @@ int pbf_slab_phase_predict(pbf_handle* h) {
   SCK(h, cudaGetLastError());
   return PBF_OK;
 }
+
+int pbf_slab_phase_predict(pbf_handle* h) { return slab_predict(h, 1); }
 
 // C. append immigrants (slots [append_base, append_base + 2*cap)), then pack the ghost layers to send
 int pbf_slab_phase_migrate(pbf_handle* h) {
@@ -448,6 +450,28 @@ static int step_p2p_once(pbf_handle* h) {
   return PBF_OK;
 }
 
+// Load-time densities (Particles::estimateDensities, particles.cpp:440-444) of a peer-mode slab: committed positions
+// re-binned, ghosts exchanged, lists INCLUDING self, one poly6 pass.  Every rank must call it.  Asynchronous.
+int pbf_slab_estimate_densities_p2p(pbf_handle* h) {
+  if (!h || !h->slab || !h->p2p) return sfail(h, PBF_ERR_INVALID, "pbf_slab_estimate_densities_p2p: not a connected peer-mode slab");
+  SCK(h, cudaSetDevice(h->device));
+  int rc;
+  if ((rc = slab_predict(h, 0)) != PBF_OK) return rc;
+  p2p_exchange_point(h);
+  if ((rc = pbf_slab_phase_migrate(h)) != PBF_OK) return rc;
+  p2p_exchange_point(h);
+  enqueue_slab_sort(h);
+  p2p_exchange_point(h);
+  h->prof_begin(K_SLAB);
+  k_fetch_peer_ranges<<<1, 32, 0, h->stream>>>(h->link, h->has_left ? h->peer[0].link : nullptr, h->has_right ? h->peer[1].link : nullptr, h->sc);
+  h->prof_end(K_SLAB); h->launches++;
+  enqueue_build(h, 1);
+  LAUNCH(h, K_DENSITY, k_density_only, blocks_for(owned_ub(h)), h->dp, 0u, 0u, h->xs_a, h->rho, h->nbr, h->slice_off, h->nbr_cnt, link_of(h));
+  h->have_neighbors = true;
+  SCK(h, cudaGetLastError());
+  return PBF_OK;
+}
+
 int pbf_slab_step_p2p(pbf_handle* h, int n_steps) {
   if (!h || !h->slab || !h->p2p || n_steps < 0) return sfail(h, PBF_ERR_INVALID, "pbf_slab_step_p2p: not a connected peer-mode slab");
   SCK(h, cudaSetDevice(h->device));
@@ -486,7 +510,7 @@ static void preload_step_kernels() {
   PL(k_cell_sort); PL(k_reorder); PL(k_build_neighbors); PL(k_alert_hist); PL(k_alert_bound); PL(k_neighbor_alert); PL(k_set_sentinel);
   PL(k_lambda); PL(k_delta<4, true>); PL(k_delta<4, false>); PL(k_delta<-1, true>); PL(k_delta<-1, false>); PL(k_velocity);
   PL(k_vorticity_xsph); PL(k_confine_commit); PL(k_write_headers); PL(k_absorb_migrants); PL(k_pack_ghosts); PL(k_absorb_ghosts);
-  PL(k_gather_bounds); PL(k_column_hist); PL(k_signal); PL(k_wait); PL(k_fetch_peer_ranges); PL(k_neighbor_digest);
+  PL(k_density_only); PL(k_gather_bounds); PL(k_column_hist); PL(k_signal); PL(k_wait); PL(k_fetch_peer_ranges); PL(k_neighbor_digest);
   PL(k_export3_f64); PL(k_export1_f64); PL(k_export3); PL(k_export1); PL(k_export_w);
 #undef PL
   cudaGetLastError();

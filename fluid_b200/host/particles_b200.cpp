@@ -21,10 +21,32 @@ Particles::Particles(double rho0, const PbfParams* params, int device, bool quie
 }
 
 Particles::~Particles() {
+  if (scratch_) pbf_destroy(scratch_);
+  if (multi_) pbf_multi_destroy(multi_);
   if (handle_) pbf_destroy(handle_);
 }
 
-const char* Particles::lastError() const { return handle_ ? pbf_last_error(handle_) : "no device handle"; }
+const char* Particles::lastError() const { return multi_ ? pbf_multi_last_error(multi_) : (handle_ ? pbf_last_error(handle_) : "no device handle"); }
+
+void Particles::setDevices(const std::vector<int>& ids) {
+  if (uploaded_) { std::cerr << "[pbf_b200] setDevices after the first step is not supported" << std::endl; std::exit(EXIT_FAILURE); }
+  devices_ = ids;
+  if (devices_.size() == 1) { device_ = devices_[0]; devices_.clear(); }
+}
+
+// Multi-device case: the surfacer and the density field run on one device, on a copy of the mirror (fp32 state widened,
+// so the copy IS the state), refreshed when a step has been taken since.
+pbf_handle* Particles::scratchHandle() {
+  if (!scratch_) {
+    if (pbf_create(&params_, devices_[0], &scratch_) != PBF_OK) { std::cerr << "[pbf_b200] pbf_create failed for the surfacer" << std::endl; std::exit(EXIT_FAILURE); }
+    scratch_step_ = -1;
+  }
+  if (scratch_step_ != steps_taken) {
+    if (pbf_upload(scratch_, ps.size(), pos_.data(), vel_.data()) != PBF_OK) { std::cerr << "[pbf_b200] " << pbf_last_error(scratch_) << std::endl; std::exit(EXIT_FAILURE); }
+    scratch_step_ = steps_taken;
+  }
+  return scratch_;
+}
 
 // (Re)create the views after the mirror arrays moved: all four containers grow together, so this runs O(log n) times.
 void Particles::rebind() {
@@ -52,6 +74,17 @@ void Particles::addParticle(Vector3D pos, Vector3D v) {
 
 void Particles::ensureUploaded() {
   if (uploaded_) return;
+  if (multi()) {
+    int rc = pbf_create_multi(&params_, (int)devices_.size(), devices_.data(), &multi_);
+    if (rc != PBF_OK) { std::cerr << "[pbf_b200] pbf_create_multi failed (code " << rc << "): no CUDA device / bad device list?" << std::endl; std::exit(EXIT_FAILURE); }
+    if ((!spheres_.empty() && pbf_multi_set_obstacle_spheres(multi_, spheres_.size() / 4, spheres_.data()) != PBF_OK) ||
+        (!tris_.empty() && pbf_multi_set_obstacle_triangles(multi_, tris_.size() / 18, tris_.data()) != PBF_OK) ||
+        pbf_multi_upload(multi_, ps.size(), pos_.data(), vel_.data()) != PBF_OK) {
+      std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE);
+    }
+    uploaded_ = true;
+    return;
+  }
   int rc = pbf_create(&params_, device_, &handle_);
   if (rc != PBF_OK) {   // the reference's error style is exit() (application.cpp:313-317); there is no CPU fallback
     std::cerr << "[pbf_b200] pbf_create failed (code " << rc << "): no CUDA device?" << std::endl;
@@ -78,7 +111,8 @@ void Particles::ensureUploaded() {
 // `ps` are views into pos_ / vel_ / rho_, so completing the transfer IS the refresh
 void Particles::refreshMirror(bool already_streamed) {
   // after a step the streaming read-back has the data on its way: pbf_sync completes it
-  int rc = already_streamed ? pbf_sync(handle_) : pbf_download(handle_, pos_.data(), vel_.data(), rho_.data());
+  int rc = multi_ ? pbf_multi_download(multi_, pos_.data(), vel_.data(), rho_.data())
+                  : (already_streamed ? pbf_sync(handle_) : pbf_download(handle_, pos_.data(), vel_.data(), rho_.data()));
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] step failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
 }
 
@@ -100,20 +134,23 @@ void Particles::reportNeighborAlerts() {
 
 void Particles::estimateDensities() {
   ensureUploaded();
-  if (pbf_estimate_densities(handle_) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  if ((multi_ ? pbf_multi_estimate_densities(multi_) : pbf_estimate_densities(handle_)) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   refreshMirror();
 }
 
 void Particles::setObstacleSpheres(const std::vector<double>& s) {
   spheres_ = s;
-  if (handle_ && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK) {
+  if (scratch_) pbf_set_obstacle_spheres(scratch_, spheres_.size() / 4, spheres_.data());
+  if ((multi_ && pbf_multi_set_obstacle_spheres(multi_, spheres_.size() / 4, spheres_.data()) != PBF_OK) ||
+      (handle_ && pbf_set_obstacle_spheres(handle_, spheres_.size() / 4, spheres_.data()) != PBF_OK)) {
     std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
   }
 }
 
 void Particles::setObstacleTriangles(const std::vector<double>& t) {
   tris_ = t;
-  if (handle_ && pbf_set_obstacle_triangles(handle_, tris_.size() / 18, tris_.data()) != PBF_OK) {
+  if ((multi_ && pbf_multi_set_obstacle_triangles(multi_, tris_.size() / 18, tris_.data()) != PBF_OK) ||
+      (handle_ && pbf_set_obstacle_triangles(handle_, tris_.size() / 18, tris_.data()) != PBF_OK)) {
     std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE);
   }
 }
@@ -127,11 +164,12 @@ void Particles::timeStep(double delta_t) {
   if (!quiet) std::cerr << "Time: " << simulate_time;          // particles.cpp:251-253
   simulate_time += delta_t;
   if (!quiet) std::cerr << " => " << simulate_time << std::endl;
-  if (pbf_step(handle_, 1) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  if ((multi_ ? pbf_multi_step(multi_, 1) : pbf_step(handle_, 1)) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
   refreshMirror(/*already_streamed=*/ps.size() > 0);
-  reportNeighborAlerts();                                        // particles.cpp:268-270 (initializeWithNewNeighbors)
+  reportNeighborAlerts();                                        // particles.cpp:268-270 (initializeWithNewNeighbors); single device only
   double ms = 0;
-  pbf_stats(handle_, &avg_rho_first_iter, &avg_rho_final, &ms);
+  if (multi_) pbf_multi_stats(multi_, &avg_rho_first_iter, &avg_rho_final, &ms);
+  else pbf_stats(handle_, &avg_rho_first_iter, &avg_rho_final, &ms);
   if (!quiet) std::cout << "avg rho: " << avg_rho_first_iter << " => " << avg_rho_final << std::endl;   // particles.cpp:267,279,295
   surfaceUpToTimestep = false;                                   // particles.cpp:296
   steps_taken++;
@@ -144,9 +182,10 @@ std::vector<Particles::SurfaceTriangle> Particles::getSurfacePrims(double isolev
   const double lo[3] = {surface_min.x, surface_min.y, surface_min.z}, hi[3] = {surface_max.x, surface_max.y, surface_max.z};
   const double grad_eps = 0.001;                                 // GRADIENT_EPS, particles.cpp:16
   size_t nt = 0;
-  if (pbf_extract_surface(handle_, lo, hi, isolevel, fStepSize, grad_eps, 0, nullptr, &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  pbf_handle* hs = multi_ ? scratchHandle() : handle_;
+  if (pbf_extract_surface(hs, lo, hi, isolevel, fStepSize, grad_eps, 0, nullptr, &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << pbf_last_error(hs) << std::endl; std::exit(EXIT_FAILURE); }
   std::vector<double> buf(18 * nt);
-  if (nt && pbf_extract_surface(handle_, lo, hi, isolevel, fStepSize, grad_eps, nt, buf.data(), &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  if (nt && pbf_extract_surface(hs, lo, hi, isolevel, fStepSize, grad_eps, nt, buf.data(), &nt) != PBF_OK) { std::cerr << "[pbf_b200] " << pbf_last_error(hs) << std::endl; std::exit(EXIT_FAILURE); }
   std::vector<SurfaceTriangle> out(nt);
   for (size_t t = 0; t < nt; t++) {
     const double* q = &buf[18 * t];
@@ -180,7 +219,8 @@ std::vector<double> Particles::estimateDensitiesAt(const std::vector<Vector3D>& 
   ensureUploaded();
   std::vector<double> q(3 * points.size()), out(points.size());
   for (size_t i = 0; i < points.size(); i++) { q[3*i] = points[i].x; q[3*i+1] = points[i].y; q[3*i+2] = points[i].z; }
-  if (pbf_density_at(handle_, points.size(), q.data(), out.data()) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  pbf_handle* hs = multi_ ? scratchHandle() : handle_;
+  if (pbf_density_at(hs, points.size(), q.data(), out.data()) != PBF_OK) { std::cerr << "[pbf_b200] " << pbf_last_error(hs) << std::endl; std::exit(EXIT_FAILURE); }
   return out;
 }
 
@@ -203,7 +243,7 @@ bool Particles::saveCheckpoint(const char* filename, std::string* error) const {
   return ok;
 }
 
-Particles* Particles::loadCheckpoint(const char* filename, std::string* error, int device, bool quiet_ctor) {
+Particles* Particles::loadCheckpoint(const char* filename, std::string* error, int device, bool quiet_ctor, const std::vector<int>* devices) {
   auto fail = [&](const std::string& m) -> Particles* { if (error) *error = m; return nullptr; };
   FILE* f = fopen(filename, "rb");
   if (!f) return fail(std::string("cannot open ") + filename);
@@ -224,6 +264,7 @@ Particles* Particles::loadCheckpoint(const char* filename, std::string* error, i
   fclose(f);
   if (!ok) return fail("truncated checkpoint");
   Particles* ps = new Particles(rho0, &prm, device, quiet_ctor);
+  if (devices) ps->setDevices(*devices);
   for (int64_t i = 0; i < n; i++)
     ps->addParticle(Vector3D(buf[3*i], buf[3*i+1], buf[3*i+2]), Vector3D(buf[3*n + 3*i], buf[3*n + 3*i+1], buf[3*n + 3*i+2]));
   for (int64_t i = 0; i < n; i++) ps->rho_[i] = buf[6*n + i];
@@ -244,7 +285,7 @@ std::string Particles::paramsString() const {
      << "\tTensile artificial pressure exponent N: " << params_.n_corr << std::endl
      << "\tVorticity confinement coefficient epsilon: " << params_.vort_eps << std::endl
      << "\tViscosity coefficient C: " << params_.visc_c << std::endl
-     << "\tBackend: B200 CUDA (libpbf_b200), fp32, Jacobi XSPH" << std::endl;
+     << "\tBackend: B200 CUDA (libpbf_b200), fp32, Jacobi XSPH" << (multi() ? ", " + std::to_string(devices_.size()) + " x-slabs" : std::string()) << std::endl;
   return ss.str();
 }
 
@@ -314,10 +355,11 @@ bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::ve
   return true;
 }
 
-Particles* load_particles_xml(const char* filename, std::string* error, const PbfParams* params, int device, bool quiet) {
+Particles* load_particles_xml(const char* filename, std::string* error, const PbfParams* params, int device, bool quiet, const std::vector<int>* devices) {
   std::vector<double> pos, vel; double rho0 = 1000.0;
   if (!parse_particles_xml(filename, pos, vel, rho0, error)) return nullptr;
   Particles* particles = new Particles(rho0, params, device, quiet);
+  if (devices) particles->setDevices(*devices);
   const size_t n = pos.size() / 3;
   for (size_t i = 0; i < n; i++)
     particles->addParticle(Vector3D(pos[3*i], pos[3*i+1], pos[3*i+2]), Vector3D(vel[3*i], vel[3*i+1], vel[3*i+2]));

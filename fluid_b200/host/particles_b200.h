@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/pbf_b200.h"
+#include "../../include/pbf_b200_multi.h"
 
 namespace pbfhost {
 
@@ -72,6 +73,12 @@ struct Particles {
   Particles(const Particles&) = delete;
   Particles& operator=(const Particles&) = delete;
 
+  // Several GPUs of one box: call before the first step / estimateDensities.  With more than one device
+  // the fluid is cut into x-slabs, one per device, behind the same object (pbf_create_multi, include/pbf_b200_multi.h):
+  // halos and migrating particles travel as peer stores over NVLink, the slabs are re-balanced as the fluid flows, and
+  // the result is bit-identical to one device.  An id may repeat (several slabs on one GPU; for testing).
+  void setDevices(const std::vector<int>& device_ids);
+  int numDevices() const { return devices_.empty() ? 1 : (int)devices_.size(); }
   void addParticle(Vector3D pos, Vector3D v);    // particles.h:118-120
   void timeStep(double delta_t);                 // particles.cpp:250-297 (delta_t must equal params.dt)
   void timeStep();                               // particles.cpp:299-301
@@ -96,7 +103,8 @@ struct Particles {
   // a pure function of (positions, velocities, ids), so a run continued from a checkpoint is bit-identical to
   // the uninterrupted run.
   bool saveCheckpoint(const char* filename, std::string* error = nullptr) const;
-  static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false);   // nullptr on error
+  static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false,
+                                   const std::vector<int>* devices = nullptr);   // nullptr on error
   long long steps_taken = 0;
   std::string paramsString() const;              // particles.cpp:420-438
   // the two numbers of the reference's "avg rho: a => b" line for the last step
@@ -112,6 +120,12 @@ struct Particles {
   PbfParams params_;
   int device_;
   pbf_handle* handle_ = nullptr;
+  pbf_multi* multi_ = nullptr;         // set instead of handle_ when setDevices named more than one device
+  std::vector<int> devices_;
+  bool multi() const { return devices_.size() > 1; }
+  // surfacer / density field in the multi-device case: a temporary single-device handle holding the mirror
+  pbf_handle* scratchHandle();
+  pbf_handle* scratch_ = nullptr; long long scratch_step_ = -1;
   bool uploaded_ = false;
   // the mirror: AoS xyz doubles in original particle order (Vector3D-compatible), what pbf_upload reads and the
   // streaming read-back writes; `ps` holds views into them (storage_ = the view objects, contiguous)
@@ -122,8 +136,11 @@ struct Particles {
 // Application::load_particles (application.cpp:302-344): <particles><density>rho0</density><ps>
 // <particle><pos>x y z</pos><v>x y z</v></particle>...  Density goes through float like stof (Q17).
 // Streaming reader (no DOM), so multi-million-particle files are fine.  Returns nullptr on error.
-Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0, bool quiet = false);
-inline Particles* load_checkpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false) { return Particles::loadCheckpoint(filename, error, device, quiet); }
+Particles* load_particles_xml(const char* filename, std::string* error = nullptr, const PbfParams* params = nullptr, int device = 0, bool quiet = false,
+                              const std::vector<int>* devices = nullptr);
+inline Particles* load_checkpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false, const std::vector<int>* devices = nullptr) {
+  return Particles::loadCheckpoint(filename, error, device, quiet, devices);
+}
 // parse only: positions / velocities (AoS doubles) and rho0; false on error
 bool parse_particles_xml(const char* filename, std::vector<double>& pos, std::vector<double>& vel, double& rho0, std::string* error);
 

@@ -7,6 +7,8 @@
 //           [--tris file]                 obstacle triangles (int64 count, then p1 p2 p3 n1 n2 n3 as 18 doubles each)
 //           [--surface file]              after the last step: updateSurface() (marching cubes on the GPU), int64 count + 18 doubles
 //                                         per triangle (p1 p2 p3 n1 n2 n3), the layout of oracle/ref_harness --surface
+//           [--gpus N | --devices a,b,c]  several GPUs behind the same Particles object: x-slabs, halos by peer stores over NVLink
+//                                         (pbf_create_multi); bit-identical to one GPU.  --box x0 y0 z0 x1 y1 z1 replaces the Cornell box
 //           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
@@ -23,7 +25,8 @@ using namespace pbfhost;
 int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
-  std::vector<double> spheres;
+  std::vector<double> spheres, box;
+  std::vector<int> devices;
   const char* trisfile = nullptr; const char* surffile = nullptr;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -33,6 +36,9 @@ int main(int argc, char** argv) {
     else if (a == "--iterations" && i + 1 < argc) iterations = atoi(argv[++i]);
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
     else if (a == "--sphere" && i + 4 < argc) { for (int k = 0; k < 4; k++) spheres.push_back(atof(argv[++i])); }   // obstacle sphere cx cy cz r, repeatable
+    else if (a == "--gpus" && i + 1 < argc) { const int g = atoi(argv[++i]); devices.clear(); for (int d = 0; d < g; d++) devices.push_back(d); }
+    else if (a == "--devices" && i + 1 < argc) { devices.clear(); for (char* t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t)); }
+    else if (a == "--box" && i + 6 < argc) { for (int k = 0; k < 6; k++) box.push_back(atof(argv[++i])); }   // simulation box instead of the Cornell box
     else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];            // obstacle triangles: int64 count + 18 doubles each
     else if (a == "--surface" && i + 1 < argc) surffile = argv[++i];          // marching-cubes surface of the final state
     else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
@@ -56,11 +62,14 @@ int main(int argc, char** argv) {
   }
   PbfParams prm; pbf_default_params(&prm);
   if (iterations >= 0) prm.iterations = iterations;
+  if (box.size() == 6) { for (int k = 0; k < 3; k++) { prm.box_min[k] = box[k]; prm.box_max[k] = box[3 + k]; } prm.y_light = box[4]; prm.z_front = box[5]; }
+  const std::vector<int>* devs = devices.empty() ? nullptr : &devices;
   printf("[Fluid Simulation] Loading particle file...");
-  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0, quiet) : load_particles_xml(pfile, &err, &prm, 0, quiet);
+  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0, quiet, devs) : load_particles_xml(pfile, &err, &prm, 0, quiet, devs);
   if (!ps) { printf("[ERROR] %s: %s\n", load_state ? "checkpoint error" : "XML error", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
   printf("Done!\n");
   ps->quiet = quiet;
+  if (box.size() == 6) { ps->surface_min = Vector3D(box[0], box[1], box[2]); ps->surface_max = Vector3D(box[3], box[4], box[5]); }   // the surfacer's lattice follows the box
   if (!spheres.empty()) ps->setObstacleSpheres(spheres);
   if (trisfile) {
     FILE* tf = fopen(trisfile, "rb");
@@ -113,8 +122,8 @@ int main(int argc, char** argv) {
     fprintf(stderr, "including %lld marching cube surfacing triangles\n", (long long)nt);   // pathtracer.cpp:250
   }
   if (save_state && !ps->saveCheckpoint(save_state, &err)) { printf("[ERROR] %s\n", err.c_str()); return EXIT_FAILURE; }
-  fprintf(stderr, "{\"n\": %lld, \"steps\": %d, \"seconds_total\": %.6f, \"ms_per_step_incl_readback\": %.4f}\n", (long long)n, done, secs,
-          done ? 1e3 * secs / done : 0.0);
+  fprintf(stderr, "{\"n\": %lld, \"steps\": %d, \"devices\": %d, \"seconds_total\": %.6f, \"ms_per_step_incl_readback\": %.4f}\n", (long long)n, done,
+          ps->numDevices(), secs, done ? 1e3 * secs / done : 0.0);
   delete ps;
   return 0;
 }

@@ -11,6 +11,7 @@
  *
  *   Particles::Particles(rho0)         -> pbf_create_multi         particles.h:114-116
  *   addParticle x N                    -> pbf_multi_upload         particles.h:118-120
+ *   estimateDensities()                -> pbf_multi_estimate_densities   particles.cpp:440-444
  *   timeStep()                         -> pbf_multi_step           particles.cpp:250-301
  *   ps[i]->getPosition() ...           -> pbf_multi_download       particles.h:21,36-42
  *   "avg rho: a => b"                  -> pbf_multi_stats          particles.cpp:267,279,295
@@ -42,6 +43,7 @@ int  pbf_multi_set_obstacle_triangles(pbf_multi* m, size_t count, const double* 
  * and connects the slabs.  A later upload re-plans from scratch. */
 int  pbf_multi_upload(pbf_multi* m, size_t n, const double* pos_xyz, const double* vel_xyz);
 int  pbf_multi_step(pbf_multi* m, int n_steps);          /* asynchronous on every device */
+int  pbf_multi_estimate_densities(pbf_multi* m);         /* Particles::estimateDensities (particles.cpp:440-444); asynchronous */
 int  pbf_multi_sync(pbf_multi* m);                       /* waits for all devices; reports deferred device-side errors */
 int  pbf_multi_download(pbf_multi* m, double* pos_xyz, double* vel_xyz, double* density);   /* original order; syncs */
 size_t pbf_multi_num_particles(pbf_multi* m);

@@ -85,6 +85,9 @@ int pbf_slab_p2p_export(pbf_handle* h, void* blob_out);
 int pbf_slab_p2p_connect_ipc(pbf_handle* h, const void* left_blob, const void* right_blob);
 int pbf_slab_set_wait_timeout(pbf_handle* h, double seconds);
 int pbf_slab_step_p2p(pbf_handle* h, int n_steps);                    /* asynchronous */
+/* Particles::estimateDensities (particles.cpp:440-444) across the slabs: densities of the committed positions, self included.
+ * Every rank calls it; asynchronous. */
+int pbf_slab_estimate_densities_p2p(pbf_handle* h);
 /* Synchronises and returns b0, b1, b2, b3, n of the last sort (peer mode keeps them on the device during the step). */
 int pbf_slab_refresh_ranges(pbf_handle* h, uint32_t bounds_out[5]);
 

@@ -174,3 +174,31 @@ def test_cli_neighbor_count_warnings(tmp_path):
     low2 = np.flatnonzero(cnt2 < 18)
     m = wr.value
     assert tot.value == len(low2) and 0 < m <= 16 and np.array_equal(ids[:m], low2[:m]) and np.array_equal(cn[:m], cnt2[ids[:m]])
+
+
+@pytest.mark.gpu
+def test_cli_several_gpus_equal_one(tmp_path):
+    """`pbf_run --devices a,b,c` (pbfhost::Particles::setDevices -> pbf_create_multi): the reference's load / estimateDensities /
+    timeStep loop on x-slabs behind the same object equals the one-device run bit for bit (positions, velocities, densities
+    of every step, the load-time densities included), obstacle sphere on a slab boundary, marching-cubes surface too."""
+    import torch
+    exe = _build()
+    from helpers import lattice_block
+    ng = torch.cuda.device_count()
+    pos, vel = lattice_block(60, 14, 12, origin=(0.1, 0.1, 0.1), spacing=0.1, v0=(0.8, -1.0, 0.0), jitter=0.001, seed=3)
+    xml = str(tmp_path / "tank.xml")
+    _write_xml(xml, pos, vel, 700.0)
+    box = ["--box", "0", "0", "0", "9.3", "3.0", "1.5"]
+    sph = ["--sphere", "3.05", "0.5", "0.7", "0.45"]
+    outs = {}
+    for tag, dev in (("one", None), ("three", ",".join(str(d % ng) for d in range(3)))):
+        dump = str(tmp_path / f"{tag}.bin"); surf = str(tmp_path / f"{tag}.surf")
+        cmd = [exe, "-p", xml, "--steps", "5", "--dump", dump, "--surface", surf, "--quiet"] + box + sph + (["--devices", dev] if dev else [])
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        info = json.loads(r.stderr.strip().splitlines()[-1])
+        assert info["devices"] == (3 if dev else 1) and info["n"] == len(pos)
+        outs[tag] = (read_dump(dump), open(surf, "rb").read())
+    for a, b in zip(outs["one"][0], outs["three"][0]):
+        assert np.array_equal(a["state"], b["state"])
+    assert outs["one"][1] == outs["three"][1] and len(outs["one"][1]) > 8
