@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpbf_b200.so")
 SOURCES = ["pbf_api.cu", "pbf_kernels.cu", "pbf_multi.cpp"]   # pbf_kernels.cu includes pbf_slab.inl and pbf_surface.inl; pbf_multi.cpp is host-only
-HEADERS = ["pbf_internal.h", "pbf_device.cuh", "pbf_slab.inl", "pbf_surface.inl", "pbf_mc_table.h", os.path.join("..", "..", "include", "pbf_b200.h"),
+HEADERS = ["pbf_internal.h", "pbf_device.cuh", "pbf_slab.inl", "pbf_surface.inl", "pbf_probe.inl", "pbf_mc_table.h", os.path.join("..", "..", "include", "pbf_b200.h"),
            os.path.join("..", "..", "include", "pbf_b200_slab.h"), os.path.join("..", "..", "include", "pbf_b200_multi.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

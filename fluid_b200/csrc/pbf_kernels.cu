@@ -1178,3 +1178,4 @@ void enqueue_digest(Solver* h, unsigned long long* digest, uint32_t* count) {
 
 #include "pbf_slab.inl"
 #include "pbf_surface.inl"
+#include "pbf_probe.inl"

@@ -580,6 +580,19 @@ int pbf_slab_p2p_connect_ipc(pbf_handle* h, const void* left_blob, const void* r
   h->p2p = true;
   return PBF_OK;
 }
+// Back to the host-driven protocol (a driver falls back to it when some rank could not map its neighbours).
+int pbf_slab_p2p_disconnect(pbf_handle* h) {
+  if (!h || !h->slab) return PBF_ERR_INVALID;
+  SCK(h, cudaSetDevice(h->device));
+  SCK(h, cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < 2; s++) {
+    Solver::Peer& P = h->peer[s];
+    if (P.ipc) for (void*& q : P.ipc_base) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    P = Solver::Peer();
+  }
+  h->p2p = false;
+  return PBF_OK;
+}
 int pbf_slab_set_wait_timeout(pbf_handle* h, double seconds) {
   if (!h || !(seconds > 0)) return PBF_ERR_INVALID;
   h->wait_timeout_ns = (long long)(seconds * 1e9);

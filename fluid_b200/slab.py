@@ -46,6 +46,7 @@ def _bind(lib):
         "pbf_slab_p2p_export": (i32, [vp, vp]),
         "pbf_slab_p2p_connect_ipc": (i32, [vp, vp, vp]),
         "pbf_slab_set_wait_timeout": (i32, [vp, C.c_double]),
+        "pbf_slab_p2p_disconnect": (i32, [vp]),
         "pbf_slab_step_p2p": (i32, [vp, i32]),
         "pbf_slab_set_histogram_interval": (i32, [vp, i32]),
         "pbf_slab_refresh_ranges": (i32, [vp, C.POINTER(C.c_uint32 * 5)]),
@@ -244,19 +245,38 @@ class SlabSolver:
         self.solver.n = n
 
     def _connect_p2p(self):
-        """Exchange CUDA IPC handles of the buffers the x-neighbours write into; from here on the step needs no transport."""
-        dist = self.dist
+        """Exchange CUDA IPC handles of the buffers the x-neighbours write into; from here on the step needs no transport.
+        If ANY rank cannot map its neighbours (no peer access between two GPUs, IPC refused by the container) every rank
+        falls back to the host-driven exchange over the process group (NCCL send/recv), loudly."""
+        dist, torch = self.dist, self.torch
         nb = self.lib.pbf_slab_p2p_blob_size()
         blob = C.create_string_buffer(nb)
-        self._ck(self.lib.pbf_slab_p2p_export(self.h, blob))
-        blobs = [None] * self.world
+        ok, why = 1, ""
+        if self.lib.pbf_slab_p2p_export(self.h, blob) != api.PBF_OK:
+            ok, why = 0, self.lib.pbf_last_error(self.h).decode()
+        blobs = [blob.raw if ok else None] * self.world
         if self.world > 1:
-            dist.all_gather_object(blobs, blob.raw)
-        left = C.create_string_buffer(blobs[self.left], nb) if self.left is not None else None
-        right = C.create_string_buffer(blobs[self.right], nb) if self.right is not None else None
-        self._ck(self.lib.pbf_slab_p2p_connect_ipc(self.h, left, right))
+            dist.all_gather_object(blobs, blob.raw if ok else None)
+        if ok and all(b is not None for b in blobs):
+            left = C.create_string_buffer(blobs[self.left], nb) if self.left is not None else None
+            right = C.create_string_buffer(blobs[self.right], nb) if self.right is not None else None
+            if self.lib.pbf_slab_p2p_connect_ipc(self.h, left, right) != api.PBF_OK:
+                ok, why = 0, self.lib.pbf_last_error(self.h).decode()
+        else:
+            ok = 0
         if self.world > 1:
-            dist.barrier()        # nobody steps before every neighbour is mapped
+            t = torch.tensor([ok], dtype=torch.int32)
+            t = t.to(f"cuda:{self.device}") if dist.get_backend() == "nccl" else t
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)      # also the barrier: nobody steps before every neighbour is mapped
+            all_ok = int(t.item())
+        else:
+            all_ok = ok
+        if not all_ok:
+            import sys
+            if why:
+                print(f"[fluid_b200.slab] rank {self.rank}: peer mode unavailable ({why}); falling back to the process-group exchange", file=sys.stderr, flush=True)
+            self._ck(self.lib.pbf_slab_p2p_disconnect(self.h))
+            self.transport = "staged" if self.staged else "nccl"
 
     def _map_buffers(self):
         torch = self.torch

@@ -160,6 +160,9 @@ enum { PBF_ARRAY_XSTAR = 0 /*n*3 predicted/corrected positions*/, PBF_ARRAY_LAMB
 int  pbf_debug_download_array(pbf_handle* h, int which, double* out);
 /* Keep a copy of x* right after predict+collide (PBF_ARRAY_XPRED) during subsequent steps. */
 int  pbf_debug_capture(pbf_handle* h, int on);
+/* development probe of the gather kernels on the lists of the last step (fluid_b200/csrc/pbf_probe.inl): average ms per
+ * launch over `reps` launches of probe `variant`; out4 (n x 4 floats, sorted order) optional */
+int  pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_out, float* out4);
 /* Host only (no device): the bounding-volume hierarchy pbf_set_obstacle_triangles builds over these triangles, without the
  * safety margin on the node boxes.  8 floats per node: lo.xyz, a, hi.xyz, b with the integers a, b stored as bits; a leaf
  * (b > 0) holds triangles [a, a + b) of the leaf order, an inner node (b = 0) has its children at a and a + 1.

@@ -83,6 +83,7 @@ int pbf_slab_p2p_connect_local(pbf_handle* h, pbf_handle* left, pbf_handle* righ
 size_t pbf_slab_p2p_blob_size(void);
 int pbf_slab_p2p_export(pbf_handle* h, void* blob_out);
 int pbf_slab_p2p_connect_ipc(pbf_handle* h, const void* left_blob, const void* right_blob);
+int pbf_slab_p2p_disconnect(pbf_handle* h);                           /* back to the host-driven phases (unmaps the neighbours) */
 int pbf_slab_set_wait_timeout(pbf_handle* h, double seconds);
 int pbf_slab_step_p2p(pbf_handle* h, int n_steps);                    /* asynchronous */
 /* Particles::estimateDensities (particles.cpp:440-444) across the slabs: densities of the committed positions, self included.
