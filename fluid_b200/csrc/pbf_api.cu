@@ -73,7 +73,7 @@ int pbf::fill_dev_params(const PbfParams& p, DevParams& d, std::string& err) {
   d.shi[2] = std::min(d.shi[2], d.zf - 1e-4f * (1.0f + std::fabs(d.zf)));
   if (ncell > 1.5e9) { err = "grid too large (box / h)"; return PBF_ERR_INVALID; }
   d.gdim_x_global = d.gdim[0]; d.cx_offset = 0; d.gx_lo = 0; d.gx_hi = d.gdim[0]; d.hop_left = 0; d.hop_right = 0;
-  d.n_sph = 0; d.n_sm = 148; d.n_tri = 0; d.tri = nullptr; d.bvh = nullptr; d.tri_id = nullptr;
+  d.n_sph = 0; d.n_sm = 148; d.one = 1.0f; d.n_tri = 0; d.tri = nullptr; d.bvh = nullptr; d.tri_id = nullptr;
   {   // fp32 contact rules of the obstacle triangles: same expressions (in double) as Oracle<float>'s constructor
     double m = 0;
     for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs((double)p.box_min[a]), std::fabs((double)p.box_max[a])));

@@ -41,6 +41,7 @@ struct DevParams {
   int   gdim_x_global, cx_offset, gx_lo, gx_hi, hop_left, hop_right;
   // obstacle spheres (pbf_set_obstacle_spheres): centre xyz, radius in .w; r^2 = r*r rounded once
   int   n_sm;                 // SMs of the device (tile order of the gather kernels)
+  float one;                  // 1.0f, a value the compiler cannot see (ex_is_neighbor_x2)
   // obstacle triangles (pbf_set_obstacle_triangles): 5 float4 each = p1, e1 = p2-p1, e2 = p3-p1, n1, n2, n3, sg, ngl
   // (sg = +-1 orientation of e1 x e2 against the vertex normals, ngl = |e1 x e2|), stored in the leaf order of the
   // bounding-volume hierarchy `bvh` (see ex_mesh_hit); tri_id = original index of each; tlo / thi = bounding box + margin
@@ -64,6 +65,33 @@ __device__ __forceinline__ float ex_norm2(float x, float y, float z) {
 __device__ __forceinline__ bool ex_is_neighbor(float3 a, float3 b, float h2) {
   float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
   return ex_norm2(dx, dy, dz) <= h2;
+}
+
+// The same predicate for TWO candidates b0, b1 at once with the packed fp32x2 instructions of sm_100a (FADD2 / FMUL2 / FFMA2): every
+// half of a packed operation is one IEEE round-to-nearest fp32 operation and the sequence of roundings is that of
+// ex_is_neighbor, so the two result bits are bit-identical to two scalar evaluations; the pair costs 8 issue slots
+// instead of 16.  ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although both carry an explicit .rn
+// (it does not for the scalar forms) -- one rounding less, no longer the reference's predicate.  The sums are therefore
+// written as fma(a, one, b) with `one` = 1.0f read from the kernel parameters: a value ptxas cannot see, a product that is
+// exact, hence the rounding of a + b and nothing to contract.  Returns bit 0 for b0, bit 1 for b1.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ uint32_t ex_is_neighbor_x2(unsigned long long ax2, unsigned long long ay2, unsigned long long az2,
+                                                      float b0x, float b1x, float b0y, float b1y, float b0z, float b1z, float h2,
+                                                      unsigned long long one2) {
+  unsigned long long dx, dy, dz, n2;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ax2), "l"(pack_f32x2(b0x, b1x)));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(ay2), "l"(pack_f32x2(b0y, b1y)));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(az2), "l"(pack_f32x2(b0z, b1z)));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(dx) : "l"(dx));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(dy) : "l"(dy));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(dz) : "l"(dz));
+  asm("fma.rn.f32x2 %0, %1, %3, %2;" : "=l"(n2) : "l"(dx), "l"(dy), "l"(one2));
+  asm("fma.rn.f32x2 %0, %1, %3, %2;" : "=l"(n2) : "l"(n2), "l"(dz), "l"(one2));
+  float n0, n1;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(n0), "=f"(n1) : "l"(n2));
+  return (n0 <= h2 ? 1u : 0u) | (n1 <= h2 ? 2u : 0u);
 }
 
 __device__ __forceinline__ float comp(const float3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }

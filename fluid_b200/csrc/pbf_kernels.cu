@@ -317,6 +317,7 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
   const int col = valid ? c.x * P.gdim[1] + c.y : -1;
   const int col0 = __shfl_sync(0xffffffffu, col, 0);
   bool uniform = __all_sync(0xffffffffu, !valid || col == col0) != 0 && !use_per_lane;
+  const unsigned long long PX2 = pack_f32x2(pi.x, pi.x), PY2 = pack_f32x2(pi.y, pi.y), PZ2 = pack_f32x2(pi.z, pi.z), ONE2 = pack_f32x2(P.one, P.one);
   if (uniform) {
 #pragma unroll 1
     for (int k = 0; k < 9; k++) {
@@ -336,15 +337,11 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
           const float4 xa = *reinterpret_cast<const float4*>(&stage[wid][0][g]), xb = *reinterpret_cast<const float4*>(&stage[wid][0][g + 4]);
           const float4 ya = *reinterpret_cast<const float4*>(&stage[wid][1][g]), yb = *reinterpret_cast<const float4*>(&stage[wid][1][g + 4]);
           const float4 za = *reinterpret_cast<const float4*>(&stage[wid][2][g]), zb = *reinterpret_cast<const float4*>(&stage[wid][2][g + 4]);
-          uint32_t m8 = 0;
-          if (ex_is_neighbor(pi, make_float3(xa.x, ya.x, za.x), P.h2)) m8 |= 1u;
-          if (ex_is_neighbor(pi, make_float3(xa.y, ya.y, za.y), P.h2)) m8 |= 2u;
-          if (ex_is_neighbor(pi, make_float3(xa.z, ya.z, za.z), P.h2)) m8 |= 4u;
-          if (ex_is_neighbor(pi, make_float3(xa.w, ya.w, za.w), P.h2)) m8 |= 8u;
-          if (ex_is_neighbor(pi, make_float3(xb.x, yb.x, zb.x), P.h2)) m8 |= 16u;
-          if (ex_is_neighbor(pi, make_float3(xb.y, yb.y, zb.y), P.h2)) m8 |= 32u;
-          if (ex_is_neighbor(pi, make_float3(xb.z, yb.z, zb.z), P.h2)) m8 |= 64u;
-          if (ex_is_neighbor(pi, make_float3(xb.w, yb.w, zb.w), P.h2)) m8 |= 128u;
+          // two candidates per packed instruction (FADD2 / FMUL2 / FFMA2 with a unit factor, each half rounded like the scalar __f*_rn: the EXACT regime holds)
+          uint32_t m8 = ex_is_neighbor_x2(PX2, PY2, PZ2, xa.x, xa.y, ya.x, ya.y, za.x, za.y, P.h2, ONE2);
+          m8 |= ex_is_neighbor_x2(PX2, PY2, PZ2, xa.z, xa.w, ya.z, ya.w, za.z, za.w, P.h2, ONE2) << 2;
+          m8 |= ex_is_neighbor_x2(PX2, PY2, PZ2, xb.x, xb.y, yb.x, yb.y, zb.x, zb.y, P.h2, ONE2) << 4;
+          m8 |= ex_is_neighbor_x2(PX2, PY2, PZ2, xb.z, xb.w, yb.z, yb.w, zb.z, zb.w, P.h2, ONE2) << 6;
           m |= m8 << g;
         }
         __syncwarp();

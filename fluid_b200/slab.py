@@ -252,7 +252,7 @@ class SlabSolver:
         nb = self.lib.pbf_slab_p2p_blob_size()
         blob = C.create_string_buffer(nb)
         ok, why = 1, ""
-        if self.lib.pbf_slab_p2p_export(self.h, blob) != api.PBF_OK:
+        if self.world > 1 and self.lib.pbf_slab_p2p_export(self.h, blob) != api.PBF_OK:     # a lone slab has nobody to export to
             ok, why = 0, self.lib.pbf_last_error(self.h).decode()
         blobs = [blob.raw if ok else None] * self.world
         if self.world > 1:
@@ -273,6 +273,7 @@ class SlabSolver:
             all_ok = ok
         if not all_ok:
             import sys
+            self.p2p_fallback_reason = why or "another rank could not map its neighbours"
             if why:
                 print(f"[fluid_b200.slab] rank {self.rank}: peer mode unavailable ({why}); falling back to the process-group exchange", file=sys.stderr, flush=True)
             self._ck(self.lib.pbf_slab_p2p_disconnect(self.h))

@@ -90,7 +90,7 @@ def main():
     else:
         owned = [int(s.n_owned())]
     out = {"world": world, "n": int(n), "steps": args.steps, "bounds": list(s.bounds), "col_bounds": list(map(int, s.col_bounds)),
-           "transport": s.transport, "n_rebalances": s.n_rebalances, "owned": owned}
+           "transport": s.transport, "p2p_fallback_reason": getattr(s, "p2p_fallback_reason", None), "n_rebalances": s.n_rebalances, "owned": owned}
     if rank == 0:
         g = api.Solver(api.default_params(**prm), device=local)
         g.set_obstacle_spheres(spheres)
