@@ -36,6 +36,14 @@ k_pack_positions(uint32_t n, const float4* __restrict__ xs, uint2* __restrict__ 
   out8[i] = pk_record(p.x, p.y, p.z, inv_period);
   out4[i] = p.w;
 }
+// probes 16 / 18: plain fp32 coordinates in two narrower arrays: (x, y) as float2 in out8 and z (16) or (z, lambda) (18, out8b) beside it
+__global__ void __launch_bounds__(TPB)
+k_split_positions(uint32_t n, const float4* __restrict__ xs, float2* __restrict__ xy, float* __restrict__ z, float2* __restrict__ zl) {
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i > n) return;
+  const float4 p = xs[i];
+  xy[i] = make_float2(p.x, p.y); z[i] = p.z; zl[i] = make_float2(p.z, p.w);
+}
 // own offsets o = q_i - 2^20 per axis; decode of a neighbour's record gives the magic floats 2^23 + ((q_j - o) mod 2^21),
 // and K - that = (q_i - q_j) wrapped into [-2^20, 2^20), exactly.
 struct PkOwn { uint32_t ox, oy, oz; };
@@ -60,7 +68,8 @@ template <int V, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
 k_probe(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs16, const uint2* __restrict__ xs8, const float* __restrict__ xs4,
         const float4* __restrict__ xv, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off,
-        const uint32_t* __restrict__ nbr_cnt, float4* __restrict__ out, float pk_scale /* Pd 2^-21 */, uint32_t rt_mask, uint32_t rt_magic) {
+        const uint32_t* __restrict__ nbr_cnt, float4* __restrict__ out, float pk_scale /* Pd 2^-21 */, uint32_t rt_mask, uint32_t rt_magic,
+        const float2* __restrict__ zl = nullptr) {
   const uint32_t t = tile_of_block(P) * TPB + threadIdx.x;
   if (t >= n) return;
   if (V <= 5) {
@@ -100,6 +109,46 @@ k_probe(const __grid_constant__ DevParams P, uint32_t n, const float4* __restric
     PBF_FOR_NEIGHBORS(t, BODY_Q)
 #undef BODY_Q
     out[t] = make_float4(w3s, gx + gy, gz, dsum);
+    return;
+  }
+  if (V == 16) {   // the shipped lambda arithmetic, neighbour coordinates gathered as float2 (x, y) + float z
+    const float2* __restrict__ xy = reinterpret_cast<const float2*>(xs8);
+    float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
+#define BODY_16(J)                                                                                     \
+    {                                                                                                  \
+      const float2 a = __ldg(&xy[J]); const float zj = __ldg(&xs4[J]);                                 \
+      const float dx = pi.x - a.x, dy = pi.y - a.y, dz = pi.z - zj;                                    \
+      float r2, w3, g;                                                                                 \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                                            \
+      w3s += w3;                                                                                       \
+      gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz);                                \
+      dsum = fmaf(g * g, r2, dsum);                                                                    \
+    }
+    PBF_FOR_NEIGHBORS(t, BODY_16)
+#undef BODY_16
+    const float rho = P.poly6_c * w3s, gs = P.spiky_c * P.inv_rho0, Gx = gs * gx, Gy = gs * gy, Gz = gs * gz;
+    const float denom = gs * gs * dsum + (Gx * Gx + Gy * Gy + Gz * Gz);
+    out[t] = make_float4(rho, -(rho * P.inv_rho0 - 1.f) / (denom + P.eps_relax), 0.f, 0.f);
+    return;
+  }
+  if (V == 18 || V == 19) {   // the shipped delta-p sum: 18 = (x, y) + (z, lambda) as two float2 gathers, 19 = one float4 gather (reference point)
+    const float2* __restrict__ xy = reinterpret_cast<const float2*>(xs8);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#define BODY_18(J)                                                                                     \
+    {                                                                                                  \
+      float4 pj;                                                                                       \
+      if (V == 18) { const float2 a = __ldg(&xy[J]); const float2 b = __ldg(&zl[J]); pj = make_float4(a.x, a.y, b.x, b.y); } \
+      else pj = __ldg(&xs16[J]);                                                                       \
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;                                \
+      float r2, w3, g;                                                                                 \
+      pair_terms(P, dx, dy, dz, r2, w3, g);                                                            \
+      const float q = P.tscale_c * w3, q2 = q * q;                                                     \
+      const float f = (pi.w + pj.w - P.kcorr * (q2 * q2)) * g;                                         \
+      ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az);                                \
+    }
+    PBF_FOR_NEIGHBORS(t, BODY_18)
+#undef BODY_18
+    out[t] = make_float4(ax, ay, az, 0.f);
     return;
   }
   const PkOwn own = pk_own(xs8[t]);
@@ -303,6 +352,11 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
   if (cudaMalloc((void**)&xs8, ((size_t)n + 32) * 8) != cudaSuccess || cudaMalloc((void**)&xs4, ((size_t)n + 32) * 4) != cudaSuccess ||
       cudaMalloc((void**)&out, (size_t)n * 16) != cudaSuccess) { cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaGetLastError(); return PBF_ERR_CUDA; }
   cudaStreamSynchronize(h->stream);
+  float2* zl = nullptr;
+  if (variant >= 16 && variant <= 19) {
+    if (cudaMalloc((void**)&zl, ((size_t)n + 32) * 8) != cudaSuccess) { cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaGetLastError(); return PBF_ERR_CUDA; }
+    k_split_positions<<<blocks_for((size_t)n + 1), TPB, 0, h->stream>>>(n, h->xs_a, reinterpret_cast<float2*>(xs8), xs4, zl);
+  } else
   k_pack_positions<<<blocks_for((size_t)n + 1), TPB, 0, h->stream>>>(n, h->xs_a, xs8, xs4, 1.f / period);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const float scale = period / 2097152.0f;
@@ -312,6 +366,9 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
 #define PROBE(V) k_probe<V, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u)
     switch (variant) {
       case 0: PROBE(0); break; case 1: PROBE(1); break; case 2: PROBE(2); break; case 3: PROBE(3); break; case 4: PROBE(4); break;
+      case 16: k_probe<16, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
+      case 18: k_probe<18, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
+      case 19: k_probe<19, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 5: PROBE(5); break; case 7: PROBE(7); break; case 8: PROBE(8); break; case 9: PROBE(9); break; case 10: PROBE(10); break; case 12: PROBE(12); break; case 13: PROBE(13); break;
 #define PROBE_B(V, B) case V * 10 + B: k_probe<V, B><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u); break;
       PROBE_B(10, 3) PROBE_B(10, 4) PROBE_B(10, 5) PROBE_B(10, 6) PROBE_B(12, 3) PROBE_B(12, 4) PROBE_B(12, 5) PROBE_B(12, 6)
@@ -329,7 +386,7 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
   if (ms_out) *ms_out = ms / reps;
   if (out4 && e == cudaSuccess) cudaMemcpy(out4, out, (size_t)n * 16, cudaMemcpyDeviceToHost);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(xs8); cudaFree(xs4); cudaFree(out);
+  cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaFree(zl);
   if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { h->last_error = cudaGetErrorString(e); return PBF_ERR_CUDA; }
   return PBF_OK;
 }
