@@ -9,6 +9,8 @@
 //                                         per triangle (p1 p2 p3 n1 n2 n3), the layout of oracle/ref_harness --surface
 //           [--gpus N | --devices a,b,c]  several GPUs behind the same Particles object: x-slabs, halos by peer stores over NVLink
 //                                         (pbf_create_multi); bit-identical to one GPU.  --box x0 y0 z0 x1 y1 z1 replaces the Cornell box
+//           [--block nx ny nz [--rho0 r]] instead of -p: a pgen.py-style lattice block (spacing 0.1 from (0.1, 0.1, 0.1), v = (0, -1, 0), index order
+//                                         x outer / z inner, particles/pgen.py:54-61) generated in memory -- a 128M-particle XML file is 10 GB of text
 //           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
@@ -25,7 +27,7 @@ using namespace pbfhost;
 int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
   double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
-  std::vector<double> spheres, box;
+  std::vector<double> spheres, box; long long blk[3] = {0, 0, 0}; double blk_rho0 = 700.0;
   std::vector<int> devices;
   const char* trisfile = nullptr; const char* surffile = nullptr;
   for (int i = 1; i < argc; i++) {
@@ -39,6 +41,8 @@ int main(int argc, char** argv) {
     else if (a == "--gpus" && i + 1 < argc) { const int g = atoi(argv[++i]); devices.clear(); for (int d = 0; d < g; d++) devices.push_back(d); }
     else if (a == "--devices" && i + 1 < argc) { devices.clear(); for (char* t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t)); }
     else if (a == "--box" && i + 6 < argc) { for (int k = 0; k < 6; k++) box.push_back(atof(argv[++i])); }   // simulation box instead of the Cornell box
+    else if (a == "--block" && i + 3 < argc) { for (int k = 0; k < 3; k++) blk[k] = atoll(argv[++i]); }
+    else if (a == "--rho0" && i + 1 < argc) blk_rho0 = atof(argv[++i]);
     else if (a == "--tris" && i + 1 < argc) trisfile = argv[++i];            // obstacle triangles: int64 count + 18 doubles each
     else if (a == "--surface" && i + 1 < argc) surffile = argv[++i];          // marching-cubes surface of the final state
     else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
@@ -47,7 +51,8 @@ int main(int argc, char** argv) {
     else if (a == "--parse-only") parse_only = true;
     else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--sphere cx cy cz r]...\n"); return 2; }
   }
-  if (!pfile && !load_state) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
+  const bool have_block = blk[0] > 0 && blk[1] > 0 && blk[2] > 0;
+  if (!pfile && !load_state && !have_block) { printf("[Warning] Particle file not passed in or not found\n[Warning] use -p <particle_file_path>\n"); return 2; }
   std::string err;
   if (parse_only && !pfile) { printf("[ERROR] --parse-only needs -p <particle_file_path>\n"); return 2; }
   if (load_state && iterations >= 0) { printf("[ERROR] --iterations cannot be combined with --load-state (the checkpoint carries its parameters)\n"); return 2; }
@@ -65,7 +70,16 @@ int main(int argc, char** argv) {
   if (box.size() == 6) { for (int k = 0; k < 3; k++) { prm.box_min[k] = box[k]; prm.box_max[k] = box[3 + k]; } prm.y_light = box[4]; prm.z_front = box[5]; }
   const std::vector<int>* devs = devices.empty() ? nullptr : &devices;
   printf("[Fluid Simulation] Loading particle file...");
-  Particles* ps = load_state ? load_checkpoint(load_state, &err, 0, quiet, devs) : load_particles_xml(pfile, &err, &prm, 0, quiet, devs);
+  Particles* ps = nullptr;
+  if (have_block && !pfile && !load_state) {                   // what Application::load_particles does (application.cpp:302-344), from a generator
+    ps = new Particles(blk_rho0, &prm, 0, quiet);
+    if (devs) ps->setDevices(*devs);
+    for (long long i = 0; i < blk[0]; i++)
+      for (long long j = 0; j < blk[1]; j++)
+        for (long long k = 0; k < blk[2]; k++) ps->addParticle(Vector3D(0.1 + 0.1 * i, 0.1 + 0.1 * j, 0.1 + 0.1 * k), Vector3D(0.0, -1.0, 0.0));
+    ps->estimateDensities();
+  } else
+    ps = load_state ? load_checkpoint(load_state, &err, 0, quiet, devs) : load_particles_xml(pfile, &err, &prm, 0, quiet, devs);
   if (!ps) { printf("[ERROR] %s: %s\n", load_state ? "checkpoint error" : "XML error", err.c_str()); return EXIT_FAILURE; }   // application.cpp:313-317
   printf("Done!\n");
   ps->quiet = quiet;
