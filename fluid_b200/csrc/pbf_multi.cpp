@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pbf_b200_multi.h"
@@ -89,6 +90,10 @@ struct pbf_multi {
   std::vector<uint32_t> hist_tmp; std::vector<uint64_t> hist;
   double last_imbalance = 1.0;
   bool trace = getenv("PBF_MULTI_TRACE") != nullptr;
+  // read-back staging, one set per slab, allocated and page-locked at the first pbf_multi_download and kept: the slabs'
+  // copies then run as direct DMA, all devices at once, and every slab's scatter to original order runs on its own thread
+  struct Stage { std::vector<double> p, v, r; std::vector<uint32_t> id; };
+  std::vector<Stage> stage;
 };
 
 namespace {
@@ -101,6 +106,7 @@ void destroy_handles(pbf_multi* m) {
   for (pbf_handle* q : m->h) if (q) pbf_sync(q);       // nobody may still be writing into a neighbour that is about to go
   for (pbf_handle* q : m->h) if (q) pbf_destroy(q);
   m->h.clear(); m->planned = false;
+  m->stage.clear();                                    // registered with the handles that just went (pbf_destroy unregisters)
 }
 int create_handles(pbf_multi* m) {
   m->h.assign(m->devices.size(), nullptr);
@@ -334,21 +340,42 @@ int pbf_multi_download(pbf_multi* m, double* pos_xyz, double* vel_xyz, double* d
   if (!m->planned) return m->n_total == 0 ? PBF_OK : mfail(m, PBF_ERR_INVALID, "nothing uploaded");
   int rc = pbf_multi_sync(m);
   if (rc != PBF_OK) return rc;
-  const size_t cap = m->particle_cap;
-  std::vector<double> sp(pos_xyz ? 3 * cap : 0), sv(vel_xyz ? 3 * cap : 0), sr(density ? cap : 0); std::vector<uint32_t> sid(cap);
-  size_t seen = 0;
-  for (size_t d = 0; d < m->h.size(); d++) {
+  const size_t cap = m->particle_cap, nd = m->h.size();
+  if (m->stage.size() != nd) m->stage.assign(nd, pbf_multi::Stage());
+  for (size_t d = 0; d < nd; d++) {                    // staging of a slab: sized once, page-locked once (a refused registration only costs speed)
+    pbf_multi::Stage& st = m->stage[d];
+    if (pos_xyz && st.p.size() < 3 * cap) { st.p.resize(3 * cap); pbf_host_register(m->h[d], st.p.data(), 3 * cap * sizeof(double)); }
+    if (vel_xyz && st.v.size() < 3 * cap) { st.v.resize(3 * cap); pbf_host_register(m->h[d], st.v.data(), 3 * cap * sizeof(double)); }
+    if (density && st.r.size() < cap) { st.r.resize(cap); pbf_host_register(m->h[d], st.r.data(), cap * sizeof(double)); }
+    if (st.id.size() < cap) { st.id.resize(cap); pbf_host_register(m->h[d], st.id.data(), cap * sizeof(uint32_t)); }
+  }
+  std::vector<int> rcs(nd, PBF_OK); std::vector<size_t> got(nd, 0); std::vector<char> bad_id(nd, 0);
+  auto one = [&](size_t d) {
+    pbf_multi::Stage& st = m->stage[d];
     size_t k = 0;
-    rc = pbf_slab_download(m->h[d], cap, pos_xyz ? sp.data() : nullptr, vel_xyz ? sv.data() : nullptr, density ? sr.data() : nullptr, sid.data(), &k);
-    if (rc != PBF_OK) return from_handle(m, (int)d, rc);
-    for (size_t q = 0; q < k; q++) {
-      const size_t i = sid[q];
-      if (i >= m->n_total) return mfail(m, PBF_ERR_CUDA, "corrupt particle id in a slab");
-      if (pos_xyz) { pos_xyz[3*i] = sp[3*q]; pos_xyz[3*i+1] = sp[3*q+1]; pos_xyz[3*i+2] = sp[3*q+2]; }
-      if (vel_xyz) { vel_xyz[3*i] = sv[3*q]; vel_xyz[3*i+1] = sv[3*q+1]; vel_xyz[3*i+2] = sv[3*q+2]; }
-      if (density) density[i] = sr[q];
+    rcs[d] = pbf_slab_download(m->h[d], cap, pos_xyz ? st.p.data() : nullptr, vel_xyz ? st.v.data() : nullptr, density ? st.r.data() : nullptr, st.id.data(), &k);
+    if (rcs[d] != PBF_OK) return;
+    got[d] = k;
+    const size_t n_total = m->n_total;
+    for (size_t q = 0; q < k; q++) {                   // global ids are disjoint between slabs: the threads never write the same element
+      const size_t i = st.id[q];
+      if (i >= n_total) { bad_id[d] = 1; return; }
+      if (pos_xyz) { pos_xyz[3*i] = st.p[3*q]; pos_xyz[3*i+1] = st.p[3*q+1]; pos_xyz[3*i+2] = st.p[3*q+2]; }
+      if (vel_xyz) { vel_xyz[3*i] = st.v[3*q]; vel_xyz[3*i+1] = st.v[3*q+1]; vel_xyz[3*i+2] = st.v[3*q+2]; }
+      if (density) density[i] = st.r[q];
     }
-    seen += k;
+  };
+  if (nd == 1) one(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; d++) th.emplace_back(one, d);
+    for (std::thread& t : th) t.join();
+  }
+  size_t seen = 0;
+  for (size_t d = 0; d < nd; d++) {
+    if (rcs[d] != PBF_OK) return from_handle(m, (int)d, rcs[d]);
+    if (bad_id[d]) return mfail(m, PBF_ERR_CUDA, "corrupt particle id in a slab");
+    seen += got[d];
   }
   if (seen != m->n_total) return mfail(m, PBF_ERR_CUDA, "particles lost or duplicated between slabs: " + std::to_string(seen) + " of " + std::to_string(m->n_total));
   return PBF_OK;

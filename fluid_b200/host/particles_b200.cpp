@@ -103,7 +103,7 @@ void Particles::ensureUploaded() {
   }
   rc = pbf_upload(handle_, n, pos_.data(), vel_.data());
   if (rc != PBF_OK) { std::cerr << "[pbf_b200] upload failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
-  if (n) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data());   // every step streams its result into the mirror
+  if (n && mirror_each_step) { pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data()); readback_on_ = true; }   // every step streams its result into the mirror
   if (n && neighbor_alert_threshold > 0) pbf_set_neighbor_alert(handle_, neighbor_alert_threshold, std::max<size_t>(neighbor_alert_max_lines, 1));
   uploaded_ = true;
 }
@@ -164,8 +164,16 @@ void Particles::timeStep(double delta_t) {
   if (!quiet) std::cerr << "Time: " << simulate_time;          // particles.cpp:251-253
   simulate_time += delta_t;
   if (!quiet) std::cerr << " => " << simulate_time << std::endl;
+  if (handle_ && ps.size() > 0 && readback_on_ != mirror_each_step) {       // the switch was flipped between steps
+    if (mirror_each_step) pbf_set_readback(handle_, pos_.data(), vel_.data(), rho_.data()); else pbf_set_readback(handle_, nullptr, nullptr, nullptr);
+    readback_on_ = mirror_each_step;
+  }
   if ((multi_ ? pbf_multi_step(multi_, 1) : pbf_step(handle_, 1)) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
-  refreshMirror(/*already_streamed=*/ps.size() > 0);
+  if (mirror_each_step) refreshMirror(/*already_streamed=*/ps.size() > 0);
+  else {                                                                   // errors of the step still surface here, `ps` is refreshed on demand
+    mirror_stale_ = true;
+    if ((multi_ ? pbf_multi_sync(multi_) : pbf_sync(handle_)) != PBF_OK) { std::cerr << "[pbf_b200] step failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
+  }
   reportNeighborAlerts();                                        // particles.cpp:268-270 (initializeWithNewNeighbors); single device only
   double ms = 0;
   if (multi_) pbf_multi_stats(multi_, &avg_rho_first_iter, &avg_rho_final, &ms);
@@ -173,6 +181,12 @@ void Particles::timeStep(double delta_t) {
   if (!quiet) std::cout << "avg rho: " << avg_rho_first_iter << " => " << avg_rho_final << std::endl;   // particles.cpp:267,279,295
   surfaceUpToTimestep = false;                                   // particles.cpp:296
   steps_taken++;
+}
+
+void Particles::syncMirror() {
+  if (!uploaded_ || !mirror_stale_) return;
+  refreshMirror(false);
+  mirror_stale_ = false;
 }
 
 void Particles::timeStep() { timeStep(params_.dt); }             // DEFAULT_DELTA_T, particles.cpp:299-301
@@ -202,6 +216,7 @@ void Particles::updateSurface() {                                // particles.cp
 }
 
 double Particles::estimateDensityAt(Vector3D pos) const {
+  const_cast<Particles*>(this)->syncMirror();                    // mirror_each_step == false: `ps` may be behind the device
   const double H = params_.h, H2 = H * H;
   double H9 = 1; for (int i = 0; i < 9; i++) H9 *= H;
   double density = 0.0;
@@ -226,6 +241,7 @@ std::vector<double> Particles::estimateDensitiesAt(const std::vector<Vector3D>& 
 
 // ---- restart files ------------------------------------------------------------------------------
 bool Particles::saveCheckpoint(const char* filename, std::string* error) const {
+  const_cast<Particles*>(this)->syncMirror();
   FILE* f = fopen(filename, "wb");
   if (!f) { if (error) *error = std::string("cannot open ") + filename; return false; }
   const int64_t n = (int64_t)ps.size(), steps = steps_taken, psz = (int64_t)sizeof(PbfParams), ns = (int64_t)(spheres_.size() / 4),

@@ -78,6 +78,12 @@ struct Particles {
   // halos and migrating particles travel as peer stores over NVLink, the slabs are re-balanced as the fluid flows, and
   // the result is bit-identical to one device.  An id may repeat (several slabs on one GPU; for testing).
   void setDevices(const std::vector<int>& device_ids);
+  // The reference's `ps` always holds the latest state, so by default every timeStep() ends with the read-back into the
+  // mirror (streamed behind the finalize kernels on one GPU; all slabs at once on several).  A windowless run that only
+  // looks at the particles at the end (main.cpp -d: simulate, then render one frame) can switch that off and call
+  // syncMirror() when it needs `ps`: the steps then run at the device rate (at 128M particles the read-back is 7 GB per step).
+  bool mirror_each_step = true;
+  void syncMirror();
   int numDevices() const { return devices_.empty() ? 1 : (int)devices_.size(); }
   void addParticle(Vector3D pos, Vector3D v);    // particles.h:118-120
   void timeStep(double delta_t);                 // particles.cpp:250-297 (delta_t must equal params.dt)
@@ -106,6 +112,7 @@ struct Particles {
   static Particles* loadCheckpoint(const char* filename, std::string* error = nullptr, int device = 0, bool quiet = false,
                                    const std::vector<int>* devices = nullptr);   // nullptr on error
   long long steps_taken = 0;
+  bool mirror_stale_ = false, readback_on_ = false;
   std::string paramsString() const;              // particles.cpp:420-438
   // the two numbers of the reference's "avg rho: a => b" line for the last step
   double avg_rho_first_iter = 0.0, avg_rho_final = 0.0;

@@ -11,6 +11,7 @@
 //                                         (pbf_create_multi); bit-identical to one GPU.  --box x0 y0 z0 x1 y1 z1 replaces the Cornell box
 //           [--block nx ny nz [--rho0 r]] instead of -p: a pgen.py-style lattice block (spacing 0.1 from (0.1, 0.1, 0.1), v = (0, -1, 0), index order
 //                                         x outer / z inner, particles/pgen.py:54-61) generated in memory -- a 128M-particle XML file is 10 GB of text
+//           [--lazy-mirror]               read the particles back only after the last step (Particles::mirror_each_step = false); ignored with --dump
 //           [--save-state f] [--load-state f]   restart files (PBFCKPT1, particles_b200.h); a continued run is bit-identical
 #include <chrono>
 #include <cstdint>
@@ -26,7 +27,7 @@ using namespace pbfhost;
 
 int main(int argc, char** argv) {
   const char* pfile = nullptr; const char* dump = nullptr; const char* save_state = nullptr; const char* load_state = nullptr;
-  double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false;
+  double seconds = -1; int steps = -1, iterations = -1; bool quiet = false, parse_only = false, lazy = false;
   std::vector<double> spheres, box; long long blk[3] = {0, 0, 0}; double blk_rho0 = 700.0;
   std::vector<int> devices;
   const char* trisfile = nullptr; const char* surffile = nullptr;
@@ -48,6 +49,7 @@ int main(int argc, char** argv) {
     else if (a == "--save-state" && i + 1 < argc) save_state = argv[++i];   // restart file written after the last step
     else if (a == "--load-state" && i + 1 < argc) load_state = argv[++i];   // continue from a restart file instead of -p
     else if (a == "--quiet") quiet = true;
+    else if (a == "--lazy-mirror") lazy = true;
     else if (a == "--parse-only") parse_only = true;
     else { fprintf(stderr, "usage: pbf_run -p particles.xml [-d seconds | --steps N] [--dump out.bin] [--quiet] [--parse-only] [--sphere cx cy cz r]...\n"); return 2; }
   }
@@ -96,6 +98,7 @@ int main(int argc, char** argv) {
   }
   const int64_t n = (int64_t)ps->ps.size();
   if (steps < 0 && seconds < 0) steps = 1;
+  if (lazy && !dump) ps->mirror_each_step = false;
   FILE* f = dump ? fopen(dump, "wb") : nullptr;
   std::vector<std::vector<double>> frames;
   auto t0 = std::chrono::steady_clock::now();
@@ -117,6 +120,7 @@ int main(int argc, char** argv) {
     }
   }
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  ps->syncMirror();                                              // --lazy-mirror: the one read-back of the run
   if (f) {
     int64_t hdr[2] = {n, done};
     fwrite("PBFDUMP1", 1, 8, f); fwrite(hdr, 8, 2, f);

@@ -226,3 +226,22 @@ def test_cli_generated_block_equals_xml_import(tmp_path):
         dumps[tag] = read_dump(dump)
     for a, b, c in zip(dumps["xml"], dumps["block"], dumps["block2"]):
         assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["state"], c["state"])
+
+
+@pytest.mark.gpu
+def test_cli_lazy_mirror_equals_per_step_readback(tmp_path):
+    """`--lazy-mirror` (Particles::mirror_each_step = false: one read-back after the last step) leaves the same final state and
+    restart file as the default per-step read-back, on one device and on slabs."""
+    import torch
+    exe = _build()
+    ng = torch.cuda.device_count()
+    box = ["--box", "0", "0", "0", "4.5", "3.0", "1.1"]
+    files = {}
+    for tag, extra in (("eager", []), ("lazy", ["--lazy-mirror"]), ("lazy2", ["--lazy-mirror", "--devices", ",".join(str(d % ng) for d in range(2))])):
+        ck = str(tmp_path / f"{tag}.ckpt")
+        r = subprocess.run([exe, "--block", "30", "9", "8", "--steps", "4", "--save-state", ck, "--quiet"] + box + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        files[tag] = open(ck, "rb").read()
+    assert files["eager"] == files["lazy"] and len(files["eager"]) > 30 * 9 * 8 * 48
+    # the slab run stores the same particles (the checkpoint header records the device list only in memory, not in the file)
+    assert files["eager"] == files["lazy2"]
