@@ -337,6 +337,48 @@ k_probe(const __grid_constant__ DevParams P, uint32_t n, const float4* __restric
   out[t] = make_float4(rho, lambda, 0.f, 0.f);
 }
 
+// probe 20: the shipped lambda arithmetic with TWO particles per lane, the list rows of slice 2w and slice 2w + 1 interleaved: the
+// two neighbourhoods overlap by ~65 %, so the second particle's gathers should find the first one's lines in L1
+__global__ void __launch_bounds__(TPB, 4)
+k_probe_two(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs, const uint32_t* __restrict__ nbr,
+            const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt, float4* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31, w = (tile_of_block(P) * TPB + threadIdx.x) >> 5;
+  const uint32_t tA = w * 64u + lane, tB = tA + 32u;
+  if (tA >= n) return;
+  const bool hasB = tB < n;
+  const float4 pA = xs[tA], pB = hasB ? xs[tB] : pA;
+  const uint4* lA = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[tA >> 5] * 32u + lane;
+  const uint4* lB = hasB ? reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[tB >> 5] * 32u + lane : lA;
+  const uint32_t rA = (nbr_cnt[tA] + 3u) >> 2, rB = hasB ? (nbr_cnt[tB] + 3u) >> 2 : 0u, rmax = max(rA, rB);
+  float wA = 0.f, gxA = 0.f, gyA = 0.f, gzA = 0.f, dA = 0.f, wB = 0.f, gxB = 0.f, gyB = 0.f, gzB = 0.f, dB = 0.f;
+  uint4 nA = rA ? ld_list_row(lA) : make_uint4(n, n, n, n), nB = rB ? ld_list_row(lB) : make_uint4(n, n, n, n);
+#define ACC2(PI, J, W3S, GX, GY, GZ, DS)                                                               \
+  {                                                                                                    \
+    const float4 pj = __ldg(&xs[J]);                                                                   \
+    const float dx = PI.x - pj.x, dy = PI.y - pj.y, dz = PI.z - pj.z;                                  \
+    float r2, w3, g;                                                                                   \
+    pair_terms(P, dx, dy, dz, r2, w3, g);                                                              \
+    W3S += w3; GX = fmaf(g, dx, GX); GY = fmaf(g, dy, GY); GZ = fmaf(g, dz, GZ); DS = fmaf(g * g, r2, DS); \
+  }
+  for (uint32_t r = 0; r < rmax; r++) {
+    const uint4 a = nA, b = nB;
+    if (r + 1 < rA) nA = ld_list_row(lA + (size_t)(r + 1) * 32u);
+    if (r + 1 < rB) nB = ld_list_row(lB + (size_t)(r + 1) * 32u);
+    if (r < rA) { ACC2(pA, a.x, wA, gxA, gyA, gzA, dA) ACC2(pA, a.y, wA, gxA, gyA, gzA, dA) ACC2(pA, a.z, wA, gxA, gyA, gzA, dA) ACC2(pA, a.w, wA, gxA, gyA, gzA, dA) }
+    if (r < rB) { ACC2(pB, b.x, wB, gxB, gyB, gzB, dB) ACC2(pB, b.y, wB, gxB, gyB, gzB, dB) ACC2(pB, b.z, wB, gxB, gyB, gzB, dB) ACC2(pB, b.w, wB, gxB, gyB, gzB, dB) }
+  }
+#undef ACC2
+  const float gs = P.spiky_c * P.inv_rho0;
+  {
+    const float rho = P.poly6_c * wA, Gx = gs * gxA, Gy = gs * gyA, Gz = gs * gzA;
+    out[tA] = make_float4(rho, -(rho * P.inv_rho0 - 1.f) / (gs * gs * dA + (Gx * Gx + Gy * Gy + Gz * Gz) + P.eps_relax), 0.f, 0.f);
+  }
+  if (hasB) {
+    const float rho = P.poly6_c * wB, Gx = gs * gxB, Gy = gs * gyB, Gz = gs * gzB;
+    out[tB] = make_float4(rho, -(rho * P.inv_rho0 - 1.f) / (gs * gs * dB + (Gx * Gx + Gy * Gy + Gz * Gz) + P.eps_relax), 0.f, 0.f);
+  }
+}
+
 }  // namespace pbf
 
 using namespace pbf;
@@ -369,6 +411,7 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
       case 16: k_probe<16, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 18: k_probe<18, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 19: k_probe<19, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
+      case 20: k_probe_two<<<blocks_for(((size_t)n + 1) / 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
       case 5: PROBE(5); break; case 7: PROBE(7); break; case 8: PROBE(8); break; case 9: PROBE(9); break; case 10: PROBE(10); break; case 12: PROBE(12); break; case 13: PROBE(13); break;
 #define PROBE_B(V, B) case V * 10 + B: k_probe<V, B><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u); break;
       PROBE_B(10, 3) PROBE_B(10, 4) PROBE_B(10, 5) PROBE_B(10, 6) PROBE_B(12, 3) PROBE_B(12, 4) PROBE_B(12, 5) PROBE_B(12, 6)
