@@ -36,10 +36,23 @@ def rr_keep(i,js,M):      # rounds stay 8 slots long: an empty class borrows fro
             src=c if b[c] else max(range(M),key=lambda q:(len(b[q]),-q))
             out.append(b[src].pop(0))
     return np.array(out,dtype=np.int64)
+def group_greedy(i,js,M,G=8):   # groups of G consecutive neighbours; inside a group an element goes to the slot of its class if that slot is free
+    out=[]
+    for g0 in range(0,len(js),G):
+        grp=list(js[g0:g0+G]); L=len(grp)
+        slots=[None]*G; rest=[]
+        for j in grp:
+            c=int((j-i)%M)%G
+            if c<L and slots[c] is None: slots[c]=j
+            else: rest.append(j)
+        for q in range(L):
+            if slots[q] is None: slots[q]=rest.pop(0)
+        out.extend(slots[:L])
+    return np.array(out,dtype=np.int64)
 rng=np.random.default_rng(0); nw=n//32
 ws=rng.choice(np.arange(nw//4,3*nw//4),size=120,replace=False)
 res={}
-for name,fn in (("ascending",lambda i,js:js),("rr8",lambda i,js:rr(i,js,8)),("rr8 keep rounds",lambda i,js:rr_keep(i,js,8)),("rr4 (32-byte records)",lambda i,js:rr(i,js,4))):
+for name,fn in (("ascending",lambda i,js:js),("rr8",lambda i,js:rr(i,js,8)),("rr8 keep rounds",lambda i,js:rr_keep(i,js,8)),("rr4 (32-byte records)",lambda i,js:rr(i,js,4)),("groups of 8, greedy",lambda i,js:group_greedy(i,js,8,8)),("groups of 16, greedy",lambda i,js:group_greedy(i,js,8,16))):
     conf=0; conf32=0; lines=0; g=0; floor_=0
     for w in ws:
         L=[]
