@@ -344,10 +344,16 @@ int pbf_multi_download(pbf_multi* m, double* pos_xyz, double* vel_xyz, double* d
   if (m->stage.size() != nd) m->stage.assign(nd, pbf_multi::Stage());
   for (size_t d = 0; d < nd; d++) {                    // staging of a slab: sized once, page-locked once (a refused registration only costs speed)
     pbf_multi::Stage& st = m->stage[d];
-    if (pos_xyz && st.p.size() < 3 * cap) { st.p.resize(3 * cap); pbf_host_register(m->h[d], st.p.data(), 3 * cap * sizeof(double)); }
-    if (vel_xyz && st.v.size() < 3 * cap) { st.v.resize(3 * cap); pbf_host_register(m->h[d], st.v.data(), 3 * cap * sizeof(double)); }
-    if (density && st.r.size() < cap) { st.r.resize(cap); pbf_host_register(m->h[d], st.r.data(), cap * sizeof(double)); }
-    if (st.id.size() < cap) { st.id.resize(cap); pbf_host_register(m->h[d], st.id.data(), cap * sizeof(uint32_t)); }
+    auto grow = [&](auto& v, size_t count) {           // (re)allocate and page-lock; an old, smaller block is unlocked before it is freed
+      if (v.size() >= count) return;
+      if (!v.empty()) pbf_host_unregister(m->h[d], v.data());
+      v.assign(count, 0);
+      pbf_host_register(m->h[d], v.data(), count * sizeof(v[0]));
+    };
+    if (pos_xyz) grow(st.p, 3 * cap);
+    if (vel_xyz) grow(st.v, 3 * cap);
+    if (density) grow(st.r, cap);
+    grow(st.id, cap);
   }
   std::vector<int> rcs(nd, PBF_OK); std::vector<size_t> got(nd, 0); std::vector<char> bad_id(nd, 0);
   auto one = [&](size_t d) {

@@ -169,7 +169,7 @@ void Particles::timeStep(double delta_t) {
     readback_on_ = mirror_each_step;
   }
   if ((multi_ ? pbf_multi_step(multi_, 1) : pbf_step(handle_, 1)) != PBF_OK) { std::cerr << "[pbf_b200] " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
-  if (mirror_each_step) refreshMirror(/*already_streamed=*/ps.size() > 0);
+  if (mirror_each_step) { refreshMirror(/*already_streamed=*/ps.size() > 0 && readback_on_); mirror_stale_ = false; }
   else {                                                                   // errors of the step still surface here, `ps` is refreshed on demand
     mirror_stale_ = true;
     if ((multi_ ? pbf_multi_sync(multi_) : pbf_sync(handle_)) != PBF_OK) { std::cerr << "[pbf_b200] step failed: " << lastError() << std::endl; std::exit(EXIT_FAILURE); }
