@@ -379,6 +379,46 @@ k_probe_two(const __grid_constant__ DevParams P, uint32_t n, const float4* __res
   }
 }
 
+// probe 22 / 23: the shipped lambda arithmetic with TWO LANES per particle (22: lanes 2p, 2p+1; 23: lanes p, p+16): each lane walks every
+// other list row of the same particle, the partial sums meet in one shuffle step.  A warp then covers 16 particles (a smaller
+// neighbourhood for the same number of gathers), paired lanes gather adjacent list entries, and lists are padded to the longest of 16.
+template <int MODE>
+__global__ void __launch_bounds__(TPB, 6)
+k_probe_pair(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs, const uint32_t* __restrict__ nbr,
+             const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt, float4* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31, w = (tile_of_block(P) * TPB + threadIdx.x) >> 5;
+  const uint32_t p = MODE == 22 ? lane >> 1 : lane & 15, hh = MODE == 22 ? lane & 1 : lane >> 4;
+  const uint32_t t = w * 16u + p;
+  const bool valid = t < n;
+  const uint32_t tt = valid ? t : n - 1u;
+  const float4 pi = xs[tt];
+  const uint4* lst = reinterpret_cast<const uint4*>(nbr) + (size_t)slice_off[tt >> 5] * 32u + (tt & 31u);
+  const uint32_t rows = valid ? (nbr_cnt[tt] + 3u) >> 2 : 0u;
+  float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
+  uint4 nx = hh < rows ? ld_list_row(lst + (size_t)hh * 32u) : make_uint4(n, n, n, n);
+#define BODY_22(J)                                                                                     \
+  {                                                                                                    \
+    const float4 pj = __ldg(&xs[J]);                                                                   \
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;                                  \
+    float r2, w3, g;                                                                                   \
+    pair_terms(P, dx, dy, dz, r2, w3, g);                                                              \
+    w3s += w3; gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz); dsum = fmaf(g * g, r2, dsum); \
+  }
+  for (uint32_t r = hh; r < rows; r += 2u) {
+    const uint4 jj = nx;
+    if (r + 2u < rows) nx = ld_list_row(lst + (size_t)(r + 2u) * 32u);
+    BODY_22(jj.x) BODY_22(jj.y) BODY_22(jj.z) BODY_22(jj.w)
+  }
+#undef BODY_22
+  const int o = MODE == 22 ? 1 : 16;
+  w3s += __shfl_xor_sync(0xffffffffu, w3s, o); gx += __shfl_xor_sync(0xffffffffu, gx, o); gy += __shfl_xor_sync(0xffffffffu, gy, o);
+  gz += __shfl_xor_sync(0xffffffffu, gz, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if (valid && hh == 0) {
+    const float gs = P.spiky_c * P.inv_rho0, rho = P.poly6_c * w3s, Gx = gs * gx, Gy = gs * gy, Gz = gs * gz;
+    out[t] = make_float4(rho, -(rho * P.inv_rho0 - 1.f) / (gs * gs * dsum + (Gx * Gx + Gy * Gy + Gz * Gz) + P.eps_relax), 0.f, 0.f);
+  }
+}
+
 }  // namespace pbf
 
 using namespace pbf;
@@ -411,6 +451,8 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
       case 16: k_probe<16, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 18: k_probe<18, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 19: k_probe<19, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
+      case 22: k_probe_pair<22><<<blocks_for((size_t)n * 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
+      case 23: k_probe_pair<23><<<blocks_for((size_t)n * 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
       case 20: k_probe_two<<<blocks_for(((size_t)n + 1) / 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
       case 5: PROBE(5); break; case 7: PROBE(7); break; case 8: PROBE(8); break; case 9: PROBE(9); break; case 10: PROBE(10); break; case 12: PROBE(12); break; case 13: PROBE(13); break;
 #define PROBE_B(V, B) case V * 10 + B: k_probe<V, B><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u); break;
