@@ -435,7 +435,9 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "particles": n_total, "particles_per_gpu": n_local, "iterations": iters,
                            "l2_policy": "inputs larger than L2 (256 MB per float4 array vs 126 MB L2); no flush needed",
-                           "parallelism": "single GPU" if world == 1 else f"{world} x-slabs, one process per GPU, halo exchange by peer stores (CUDA IPC) + flag hand-overs"},
+                           "parallelism": "single GPU" if world == 1 else (f"{world} x-slabs, one process per GPU, halo exchange by peer stores (CUDA IPC) + flag hand-overs"
+                                                                            if getattr(solver, "transport", "") == "p2p" else
+                                                                            f"{world} x-slabs, one process per GPU, halo exchange by NCCL send/recv (transport {getattr(solver, 'transport', '?')}: peer mapping unavailable)")},
                 "wall_ms_per_step": wall_ms / args.steps, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "mean_neighbours": nb_head, "pairs_per_s": 2.0 * n_total * nb_head * iters / (ms_per_step * 1e-3), "evolved": evolved,
                 "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels}
