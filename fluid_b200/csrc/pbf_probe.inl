@@ -419,6 +419,85 @@ k_probe_pair(const __grid_constant__ DevParams P, uint32_t n, const float4* __re
   }
 }
 
+// probe 24: 16-bit list entries.  The same per-lane neighbour sequence as the shipped lists, stored as signed 16-bit DELTAS to the
+// previous entry, 8 per 16-byte row; the first entry and every jump of 2^15 or more (a change of x-column: ~1.2e5 at C4) is the
+// escape code 0x8000 and takes the absolute index from a small side array (<= 4 per particle here, counted).  Lists are NOT
+// padded with a sentinel (a delta cannot name it): the last, partial row is walked under a count.
+__global__ void __launch_bounds__(TPB)
+k_probe_pack16(uint32_t n, const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ slice_off, const uint32_t* __restrict__ nbr_cnt,
+               uint4* __restrict__ out16, uint32_t* __restrict__ off16, uint32_t* __restrict__ side, unsigned long long* __restrict__ cursor,
+               unsigned int* __restrict__ overflow) {
+  const uint32_t t = blockIdx.x * TPB + threadIdx.x, lane = threadIdx.x & 31;
+  const bool valid = t < n;
+  const uint32_t cnt = valid ? nbr_cnt[t] : 0u, rows16 = (cnt + 7u) >> 3;
+  const uint32_t rmax = __reduce_max_sync(0xffffffffu, rows16);
+  unsigned long long off = 0;
+  if (lane == 0) off = atomicAdd(cursor, (unsigned long long)rmax);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  if (!valid) return;
+  if (lane == 0) off16[t >> 5] = (uint32_t)off;
+  const uint32_t* lst = nbr + ((size_t)slice_off[t >> 5] * 32u + lane) * 4u;          // row r of this lane: lst + r * 128
+  uint32_t prev = 0, nesc = 0, buf[4] = {0, 0, 0, 0};
+  for (uint32_t k = 0; k < rows16 * 8u; k++) {
+    uint32_t e = 0;
+    if (k < cnt) {
+      const uint32_t j = lst[(size_t)(k >> 2) * 128u + (k & 3u)];
+      const long long d = (long long)j - (long long)prev;
+      if (k == 0 || d >= 32767 || d <= -32767) {
+        e = 0x8000u;
+        if (nesc < 4u) side[((size_t)(t >> 5) * 4u + nesc) * 32u + lane] = j; else atomicAdd(overflow, 1u);
+        nesc++;
+      } else e = (uint32_t)(int)d & 0xFFFFu;
+      prev = j;
+    }
+    buf[(k & 7u) >> 1] |= e << (16u * (k & 1u));
+    if ((k & 7u) == 7u) {
+      out16[(off + (k >> 3)) * 32ull + lane] = make_uint4(buf[0], buf[1], buf[2], buf[3]);
+      buf[0] = buf[1] = buf[2] = buf[3] = 0;
+    }
+  }
+}
+__global__ void __launch_bounds__(TPB)
+k_probe_lambda16(const __grid_constant__ DevParams P, uint32_t n, const float4* __restrict__ xs, const uint4* __restrict__ l16,
+                 const uint32_t* __restrict__ off16, const uint32_t* __restrict__ side, const uint32_t* __restrict__ nbr_cnt, float4* __restrict__ out) {
+  const uint32_t t = tile_of_block(P) * TPB + threadIdx.x, lane = threadIdx.x & 31;
+  if (t >= n) return;
+  const float4 pi = xs[t];
+  const uint4* lst = l16 + (size_t)off16[t >> 5] * 32u + lane;
+  const uint32_t* sd = side + (size_t)(t >> 5) * 128u + lane;
+  const uint32_t cnt = nbr_cnt[t], full = cnt >> 3, rows = (cnt + 7u) >> 3;
+  float w3s = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, dsum = 0.f;
+  uint32_t j = 0;
+#define BODY_24(J)                                                                                     \
+  {                                                                                                    \
+    const float4 pj = __ldg(&xs[J]);                                                                   \
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;                                  \
+    float r2, w3, g;                                                                                   \
+    pair_terms(P, dx, dy, dz, r2, w3, g);                                                              \
+    w3s += w3; gx = fmaf(g, dx, gx); gy = fmaf(g, dy, gy); gz = fmaf(g, dz, gz); dsum = fmaf(g * g, r2, dsum); \
+  }
+#define ENTRY_LO(W) { const int d = (int)((W) << 16) >> 16; if (d == -32768) { j = *sd; sd += 32; } else j += (uint32_t)d; BODY_24(j) }
+#define ENTRY_HI(W) { const int d = (int)(W) >> 16; if (d == -32768) { j = *sd; sd += 32; } else j += (uint32_t)d; BODY_24(j) }
+  uint4 nx = rows ? ld_list_row(lst) : make_uint4(0, 0, 0, 0);
+  for (uint32_t r = 0; r < full; r++) {
+    const uint4 w = nx;
+    if (r + 1 < rows) nx = ld_list_row(lst + (size_t)(r + 1) * 32u);
+    ENTRY_LO(w.x) ENTRY_HI(w.x) ENTRY_LO(w.y) ENTRY_HI(w.y) ENTRY_LO(w.z) ENTRY_HI(w.z) ENTRY_LO(w.w) ENTRY_HI(w.w)
+  }
+  if (full < rows) {                                       // the partial row, under a count
+    const uint32_t ww[4] = {nx.x, nx.y, nx.z, nx.w};
+    const uint32_t rem = cnt & 7u;
+#pragma unroll
+    for (uint32_t k = 0; k < 7u; k++)
+      if (k < rem) { if (k & 1u) ENTRY_HI(ww[k >> 1]) else ENTRY_LO(ww[k >> 1]) }
+  }
+#undef ENTRY_LO
+#undef ENTRY_HI
+#undef BODY_24
+  const float gs = P.spiky_c * P.inv_rho0, rho = P.poly6_c * w3s, Gx = gs * gx, Gy = gs * gy, Gz = gs * gz;
+  out[t] = make_float4(rho, -(rho * P.inv_rho0 - 1.f) / (gs * gs * dsum + (Gx * Gx + Gy * Gy + Gz * Gz) + P.eps_relax), 0.f, 0.f);
+}
+
 }  // namespace pbf
 
 using namespace pbf;
@@ -440,6 +519,21 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
     k_split_positions<<<blocks_for((size_t)n + 1), TPB, 0, h->stream>>>(n, h->xs_a, reinterpret_cast<float2*>(xs8), xs4, zl);
   } else
   k_pack_positions<<<blocks_for((size_t)n + 1), TPB, 0, h->stream>>>(n, h->xs_a, xs8, xs4, 1.f / period);
+  uint4* l16 = nullptr; uint32_t* off16 = nullptr; uint32_t* side16 = nullptr; unsigned long long* cur16 = nullptr; unsigned int* ovf16 = nullptr;
+  if (variant == 24) {
+    const size_t slices = ((size_t)n + 31) / 32, cap_rows = (size_t)n / 32 * 24 + 1024;          // rows of 32 lanes x 16 bytes: <= 192 entries / 8 per particle
+    if (cudaMalloc((void**)&l16, cap_rows * 32 * 16) != cudaSuccess || cudaMalloc((void**)&off16, slices * 4) != cudaSuccess ||
+        cudaMalloc((void**)&side16, slices * 128 * 4) != cudaSuccess || cudaMalloc((void**)&cur16, 16) != cudaSuccess) {
+      cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaFree(zl); cudaFree(l16); cudaFree(off16); cudaFree(side16); cudaFree(cur16); cudaGetLastError(); return PBF_ERR_CUDA;
+    }
+    ovf16 = reinterpret_cast<unsigned int*>(cur16 + 1);
+    cudaMemsetAsync(cur16, 0, 16, h->stream);
+    k_probe_pack16<<<blocks_for(n), TPB, 0, h->stream>>>(n, h->nbr, h->slice_off, h->nbr_cnt, l16, off16, side16, cur16, ovf16);
+    unsigned long long used[2] = {0, 0}, rows32 = 0;
+    cudaMemcpyAsync(used, cur16, 16, cudaMemcpyDeviceToHost, h->stream); cudaMemcpyAsync(&rows32, &h->sc->nbr_cursor, 8, cudaMemcpyDeviceToHost, h->stream); cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "[probe 24] 16-bit lists: %llu rows of 512 bytes = %.3f GB (32-bit lists: %.3f GB), particles with more than 4 escapes: %u\n", used[0],
+            used[0] * 512.0 / 1e9, (double)rows32 * 512.0 / 1e9, (unsigned)(used[1] & 0xFFFFFFFFull));
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const float scale = period / 2097152.0f;
   // the reference point: variant 6 = the shipped lambda kernel itself, writing (x, y, z, lambda) to `out` and rho to h->rho
@@ -451,6 +545,7 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
       case 16: k_probe<16, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 18: k_probe<18, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
       case 19: k_probe<19, 1><<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, xs8, xs4, h->xv, h->nbr, h->slice_off, h->nbr_cnt, out, scale, PK_MASK, 0x4B000000u, zl); break;
+      case 24: k_probe_lambda16<<<blocks_for(n), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, l16, off16, side16, h->nbr_cnt, out); break;
       case 22: k_probe_pair<22><<<blocks_for((size_t)n * 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
       case 23: k_probe_pair<23><<<blocks_for((size_t)n * 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
       case 20: k_probe_two<<<blocks_for(((size_t)n + 1) / 2), TPB, 0, h->stream>>>(h->dp, n, h->xs_a, h->nbr, h->slice_off, h->nbr_cnt, out); break;
@@ -471,7 +566,7 @@ extern "C" int pbf_debug_probe(pbf_handle* h, int variant, int reps, double* ms_
   if (ms_out) *ms_out = ms / reps;
   if (out4 && e == cudaSuccess) cudaMemcpy(out4, out, (size_t)n * 16, cudaMemcpyDeviceToHost);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaFree(zl);
+  cudaFree(xs8); cudaFree(xs4); cudaFree(out); cudaFree(zl); cudaFree(l16); cudaFree(off16); cudaFree(side16); cudaFree(cur16);
   if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { h->last_error = cudaGetErrorString(e); return PBF_ERR_CUDA; }
   return PBF_OK;
 }

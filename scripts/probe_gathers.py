@@ -11,7 +11,8 @@ NAMES = {0: "lists only (no gather)", 1: "gather 4 B", 2: "gather 8 B", 3: "gath
          10: "lambda, 8-byte records, packed, tuned", 11: "as 10, 6 CTAs/SM (40 registers)", 12: "as 10, next row's records in flight",
          13: "delta-p sum, 8-byte pos + 4-byte lambda, packed, pipelined", 14: "as 12, 6 CTAs/SM", 15: "as 13, 6 CTAs/SM",
          16: "k_lambda arithmetic, float2 (x, y) + float z gathers", 18: "delta-p sum, float2 (x, y) + float2 (z, lambda) gathers", 19: "delta-p sum, one float4 gather (as shipped)", 20: "k_lambda arithmetic, two particles per lane (slices 2w, 2w+1 interleaved)",
-         22: "k_lambda arithmetic, two lanes per particle (lanes 2p, 2p+1 take alternate list rows)", 23: "k_lambda arithmetic, two lanes per particle (lanes p, p+16)"}
+         22: "k_lambda arithmetic, two lanes per particle (lanes 2p, 2p+1 take alternate list rows)", 23: "k_lambda arithmetic, two lanes per particle (lanes p, p+16)",
+         24: "k_lambda arithmetic, 16-bit delta list entries (8 per 16-byte row, escapes from a side array)"}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--block", type=int, nargs=3, default=[400, 200, 200])
@@ -33,7 +34,7 @@ res = {"particles": n, "steps": args.steps, "variants": {}}
 ref = None
 for v in args.variants:
     ms = C.c_double()
-    out = np.zeros((n, 4), dtype=np.float32) if v in (6, 8, 9, 10, 12, 16, 20, 22, 23) or v // 10 in (10, 12) else None
+    out = np.zeros((n, 4), dtype=np.float32) if v in (6, 8, 9, 10, 12, 16, 20, 22, 23, 24) or v // 10 in (10, 12) else None
     rc = lib.pbf_debug_probe(g.h, v, args.reps, C.byref(ms), out.ctypes.data_as(C.c_void_p) if out is not None else None)
     if rc != 0:
         print(v, "failed", rc, lib.pbf_last_error(g.h).decode()); continue
