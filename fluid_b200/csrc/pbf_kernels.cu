@@ -293,6 +293,7 @@ k_build_neighbors(const __grid_constant__ DevParams P, uint32_t i0, uint32_t cnt
                   unsigned long long cap_rows, int include_self, Scalars* __restrict__ sc, int use_per_lane,
                   const SlabLink* __restrict__ lk) {
   if (lk) { i0 = lk->b[0]; cnt_range = lk->b[3] - lk->b[0]; sentinel = lk->b[4]; }
+  if (blockIdx.x * TPB >= cnt_range) return;             // peer mode sizes the grid for the capacity: nothing to do, and no zero-row atomics on the cursor
   const uint32_t t = blockIdx.x * TPB + threadIdx.x;     // index inside the owned range
   const uint32_t i = i0 + t;                             // index in the cell-sorted arrays
   const int lane = threadIdx.x & 31;
@@ -557,7 +558,8 @@ k_lambda(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0 /* multip
   const uint32_t t = t0 + tile_of_block(P) * TPB + threadIdx.x;
   float rho = 0.f;
   if (t < n) rho = lambda_particle(P, t, i0 + t, xs_in, xs_out, nbr, slice_off, nbr_cnt, rho_out, lk, push);
-  if (rho_sum) block_sum_to_double(rho, rho_sum);
+  // peer mode sizes the grid for the capacity: a block past the last particle must not queue its zeros on the one address every block adds to
+  if (rho_sum && t - threadIdx.x < n) block_sum_to_double(rho, rho_sum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -673,7 +675,7 @@ k_vorticity_xsph(const __grid_constant__ DevParams P, uint32_t i0, uint32_t t0, 
     vel_out[i] = make_float4(fmaf(xc, sx, vi.x), fmaf(xc, sy, vi.y), fmaf(xc, sz, vi.z), 0.f);
     rho_out[i] = rho;                                              // the density the visualiser reads
   }
-  if (rho_sum) block_sum_to_double(rho, rho_sum);
+  if (rho_sum && t - threadIdx.x < n) block_sum_to_double(rho, rho_sum);   // not from the empty blocks of a capacity-sized grid (see k_lambda)
 }
 
 __global__ void __launch_bounds__(TPB)

@@ -17,6 +17,8 @@ def main():
     steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     iters = int(sys.argv[5]) if len(sys.argv) > 5 else 12
     box_max = (max(30.0, 0.3 * nx), max(15.0, 0.15 * ny), 0.1 * nz + 0.1)
+    if os.environ.get("QB_CONFINED"):      # the wide-tank geometry of the N > 1 bench: walls right behind both x-faces of the block
+        box_max = (0.1 * nx + 0.1, 30.0, 0.1 * nz + 0.1)
     p = api.default_params(rest_density=700.0, iterations=iters, box_min=(0, 0, 0), box_max=box_max, y_light=box_max[1], z_front=box_max[2])
     s = api.Solver(p)
     if os.environ.get("QB_OBSTACLES"):      # two spheres and a cuboid standing in the block (particles inside them are left out)
