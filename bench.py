@@ -322,6 +322,17 @@ def main():
                 e.update({"algorithmic_bytes_per_particle": alg[name], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
             kernels[name] = e
     dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
+    # N > 1: what every rank spent per step in its own kernels and in the exchange-point kernels (signal + bounded wait for the
+    # neighbours), and its SM clock: the slabs run in lock step, so the slowest GPU of the chain sets the pace for all
+    per_rank = None
+    if world > 1:
+        work = sum(ms for name, (ms, cnt) in prof.items() if name != "slab") / args.steps
+        wait = prof.get("slab", (0.0, 0))[0] / args.steps
+        mine = torch.tensor([work, wait, float(clocks.get("sm_mhz") or 0.0), float(clocks.get("power_w_max") or 0.0)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernels_ms_per_step": [round(float(a[0]), 3) for a in allr], "exchange_points_ms_per_step": [round(float(a[1]), 3) for a in allr],
+                    "sm_mhz": [float(a[2]) for a in allr], "power_w_max": [float(a[3]) for a in allr]}
     traffic = None; ncu_note = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -443,6 +454,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels}
         if witness is not None:
             line["slab_equals_single"] = witness.get("slab_equals_single"); line["n_conserved"] = witness["n_conserved"]; line["witness"] = witness
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
