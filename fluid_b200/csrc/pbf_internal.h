@@ -21,7 +21,7 @@ enum { ERRBIT_NBR_CAPACITY = 1, ERRBIT_NONFINITE = 2, ERRBIT_HALO_CAPACITY = 4, 
 struct SlabLink {
   uint32_t b[8];          // b0, b1, b2, b3, n_sorted of the LAST sort: [0,b0) left ghosts | [b0,b3) owned | [b3,n) right ghosts
   uint32_t nb[2][8];      // copies of the x-neighbours' b[] for the same step (k_fetch_peer_ranges): [0] left, [1] right
-  uint32_t flag[2];       // last epoch completed by the left [0] / right [1] neighbour (written by ITS k_signal)
+  uint32_t flag[2];       // last epoch completed by the left [0] / right [1] neighbour (written by ITS k_exchange)
   uint32_t col_hist_valid, pad[5];
 };
 // where a solver pass also stores its boundary columns: the neighbours' ghost ranges of the same array (peer stores)

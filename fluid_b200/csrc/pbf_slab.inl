@@ -117,16 +117,15 @@ k_column_hist(const uint32_t* __restrict__ cell_start, uint32_t gyz, int gx_lo, 
 // A rank tells its x-neighbours that everything it enqueued before this point is complete (its kernels' stores into
 // their ghost ranges / receive buffers included: stream order + a system-scope fence), by writing the epoch into the flag
 // words they poll.  Every rank issues the same sequence of signals, so epochs agree without any host exchange.
-__global__ void k_signal(uint32_t* flag_at_left, uint32_t* flag_at_right, uint32_t epoch) {
+// ... and then waits until both neighbours have reached `epoch`: ONE launch per exchange point (a step has 2 I + 5 of them).  The
+// wait is bounded: after timeout_ns the error flag is set and this and every later exchange point of the handle return at
+// once (the step finishes with garbage and pbf_sync reports PBF_ERR_CUDA).
+__global__ void k_exchange(uint32_t* flag_at_left, uint32_t* flag_at_right, const uint32_t* flag_left, const uint32_t* flag_right, uint32_t epoch,
+                           Scalars* sc, long long timeout_ns) {
   if (threadIdx.x || blockIdx.x) return;
   __threadfence_system();
   if (flag_at_left) *reinterpret_cast<volatile uint32_t*>(flag_at_left) = epoch;
   if (flag_at_right) *reinterpret_cast<volatile uint32_t*>(flag_at_right) = epoch;
-}
-// ... and waits until both neighbours have reached `epoch`.  Bounded: after timeout_ns the error flag is set and this and
-// every later wait of the handle return at once (the step finishes with garbage and pbf_sync reports PBF_ERR_CUDA).
-__global__ void k_wait(const uint32_t* flag_left, const uint32_t* flag_right, uint32_t epoch, Scalars* sc, long long timeout_ns) {
-  if (threadIdx.x || blockIdx.x) return;
   if (*reinterpret_cast<volatile int*>(&sc->err) & ERRBIT_PEER_TIMEOUT) return;
   unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
@@ -411,18 +410,13 @@ int pbf_slab_phase_sort(pbf_handle* h, uint32_t bounds_out[5]) {
 }
 
 // ---- peer mode ----------------------------------------------------------------------------------------------------------
-static void p2p_signal(pbf_handle* h) {
+static void p2p_exchange_point(pbf_handle* h) {
   h->epoch++;
   h->prof_begin(K_SLAB);
-  k_signal<<<1, 32, 0, h->stream>>>(h->has_left ? &h->peer[0].link->flag[1] : nullptr, h->has_right ? &h->peer[1].link->flag[0] : nullptr, h->epoch);
+  k_exchange<<<1, 32, 0, h->stream>>>(h->has_left ? &h->peer[0].link->flag[1] : nullptr, h->has_right ? &h->peer[1].link->flag[0] : nullptr,
+                                      h->has_left ? &h->link->flag[0] : nullptr, h->has_right ? &h->link->flag[1] : nullptr, h->epoch, h->sc, h->wait_timeout_ns);
   h->prof_end(K_SLAB); h->launches++;
 }
-static void p2p_wait(pbf_handle* h) {
-  h->prof_begin(K_SLAB);
-  k_wait<<<1, 32, 0, h->stream>>>(h->has_left ? &h->link->flag[0] : nullptr, h->has_right ? &h->link->flag[1] : nullptr, h->epoch, h->sc, h->wait_timeout_ns);
-  h->prof_end(K_SLAB); h->launches++;
-}
-static void p2p_exchange_point(pbf_handle* h) { p2p_signal(h); p2p_wait(h); }
 
 // One whole step of a slab in peer mode: the phases above with every message written straight into the neighbour's
 // memory and every hand-over a flag, i.e. no host synchronisation and no copy engine work at all.  Asynchronous.
@@ -501,7 +495,7 @@ int pbf_slab_refresh_ranges(pbf_handle* h, uint32_t bounds_out[5]) {
 }  // extern "C"
 
 // CUDA loads a kernel's code at its first launch, and that load may have to wait until the device is idle: a rank that
-// sits in k_wait for a neighbour whose launches the (blocked) host thread has not issued yet would never be released.
+// sits in k_exchange for a neighbour whose launches the (blocked) host thread has not issued yet would never be released.
 // Everything a peer-mode step launches is therefore loaded before the first step (cudaFuncGetAttributes loads a function).
 static void preload_step_kernels() {
   cudaFuncAttributes a;
@@ -510,7 +504,7 @@ static void preload_step_kernels() {
   PL(k_cell_sort); PL(k_reorder); PL(k_build_neighbors); PL(k_alert_hist); PL(k_alert_bound); PL(k_neighbor_alert); PL(k_set_sentinel);
   PL(k_lambda); PL(k_delta<4, true>); PL(k_delta<4, false>); PL(k_delta<-1, true>); PL(k_delta<-1, false>); PL(k_velocity);
   PL(k_vorticity_xsph); PL(k_confine_commit); PL(k_write_headers); PL(k_absorb_migrants); PL(k_pack_ghosts); PL(k_absorb_ghosts);
-  PL(k_density_only); PL(k_gather_bounds); PL(k_column_hist); PL(k_signal); PL(k_wait); PL(k_fetch_peer_ranges); PL(k_neighbor_digest);
+  PL(k_density_only); PL(k_gather_bounds); PL(k_column_hist); PL(k_exchange); PL(k_fetch_peer_ranges); PL(k_neighbor_digest);
   PL(k_export3_f64); PL(k_export1_f64); PL(k_export3); PL(k_export1); PL(k_export_w);
 #undef PL
   cudaGetLastError();
